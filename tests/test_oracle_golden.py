@@ -1,0 +1,122 @@
+"""Pin the CPU oracle (oracle/reference_port.py) against vectors produced by the live
+reference (oracle/gen_golden.py -> tests/golden/*.npz).  fp64 results must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import reference_port as rp
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _grid(bounds, res):
+    b = tuple(tuple(float(v) for v in row) for row in bounds)
+    return rp.create_grid(b, tuple(int(r) for r in res))
+
+
+def test_create_grid_axes(golden_dir):
+    g = _load(golden_dir, "case_a_interp.npz")
+    (X, Y, Z), (x, y, z) = _grid(g["bounds"], g["res"])
+    assert np.array_equal(x, g["ax_x"]) and np.array_equal(y, g["ax_y"]) and np.array_equal(z, g["ax_z"])
+    assert X.shape == (9, 11, 13)
+
+
+@pytest.mark.parametrize("k", [1, 8, 50])
+def test_knn_matches_ckdtree_and_bruteforce(golden_dir, k):
+    g = _load(golden_dir, "case_a_interp.npz")
+    grid, _ = _grid(g["bounds"], g["res"])
+    fc = rp.flat_coords(grid)
+    d, i, d2 = rp.knn_canonical(g["points"], fc, k)
+    # random cloud: no ties, so canonical order == cKDTree's own order, bit for bit
+    assert np.array_equal(i, g[f"knn_i_k{k}"])
+    assert np.array_equal(d, g[f"knn_d_k{k}"])
+    db, ib, _ = rp.knn_bruteforce(g["points"], fc, k)
+    assert np.array_equal(ib, i) and np.array_equal(db, d)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("idw_k50", dict(method="idw")),
+    ("idw_k8_p3", dict(method="idw", idw_neighbors=8, idw_power=3.0)),
+    ("idw_k8_p15", dict(method="idw", idw_neighbors=8, idw_power=1.5)),
+    ("sibson_k30", dict(method="sibson")),
+    ("sibson_k12", dict(method="sibson", sibson_neighbors=12)),
+    ("rbf_k20", dict(method="rbf")),
+    ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1)),
+    ("nearest", dict(method="nearest")),
+])
+def test_interpolate_field_bitexact(golden_dir, name, kw):
+    g = _load(golden_dir, "case_a_interp.npz")
+    grid, _ = _grid(g["bounds"], g["res"])
+    U, V, W = rp.interpolate_field(g["points"], g["values"], grid, chunk_voxels=500, **kw)
+    ref = g[name]
+    assert np.array_equal(np.stack([U, V, W], 0), ref)
+
+
+def test_lattice_ties_values_and_boundary_particles(golden_dir):
+    g = _load(golden_dir, "case_b_boundary.npz")
+    b = tuple(tuple(float(v) for v in row) for row in g["bounds"])
+    for th, st in ((1, 1), (2, 1), (2, 3), (3, 5)):
+        bx, by, bz = rp.extract_boundary_particles(g["mask_raw"], b, sampling_step=st, thickness=th)
+        assert np.array_equal(np.stack([bx, by, bz], 0).astype(np.float64), g[f"bp_t{th}_s{st}"])
+    grid, _ = rp.create_grid(b, 12)
+    U, V, W = rp.interpolate_field(g["points"], g["values"], grid, method="idw", idw_neighbors=20)
+    ref = g["idw_k20"]
+    got = np.stack([U, V, W], 0)
+    # ties reorder equal-weight terms of the fp64 sums: identical up to summation order
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(got - ref)) <= 1e-12 * scale
+    for use_scipy in (True, False):
+        assert np.array_equal(rp.sample_mask_on_grid(g["mask_raw"], grid, b, use_scipy=use_scipy), g["mask_grid"])
+
+
+@pytest.mark.parametrize("name", ["same", "down2", "down3", "shift", "up"])
+def test_mask_sampling(golden_dir, name):
+    g = _load(golden_dir, "case_c_mask.npz")
+    braw = tuple(tuple(float(v) for v in row) for row in g[f"{name}_braw"])
+    bgrid = tuple(tuple(float(v) for v in row) for row in g[f"{name}_bgrid"])
+    grid, _ = rp.create_grid(bgrid, tuple(int(r) for r in g[f"{name}_res"]))
+    for use_scipy in (True, False):
+        out = rp.sample_mask_on_grid(g["mask_raw"], grid, braw, use_scipy=use_scipy)
+        assert np.array_equal(out, g[f"{name}_out"]), (name, use_scipy)
+
+
+def test_divergence_flux_stats(golden_dir):
+    g = _load(golden_dir, "case_d_divergence.npz")
+    dx, dy, dz = g["h"]
+    div = rp.compute_consistent_divergence(g["u"], g["v"], g["w"], g["mask"], dx, dy, dz)
+    assert np.array_equal(div, g["div"])
+    assert np.array_equal(rp.flux_xy(g["w"], dx, dy), g["q_xy"])
+    assert np.array_equal(rp.flux_xz(g["v"], dx, dz), g["q_xz"])
+    assert np.array_equal(rp.flux_yz(g["u"], dy, dz), g["q_yz"])
+    assert rp.mid_plane_x_flux(g["u"], dy, dz) == g["mid_x"]
+    assert rp.mean_abs_div(div, g["mask"]) == g["mean_abs_div"]
+
+
+def test_known_answers():
+    # constant field -> constant; voxel on a particle returns its value
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(0, 9, size=(200, 3)).astype(np.float32).astype(np.float64)
+    pts[0] = (4.0, 4.0, 4.0)
+    vals = np.full((200, 3), 7.0)
+    grid, _ = rp.create_grid(((0, 10), (0, 10), (0, 10)), 10)
+    U, V, W = rp.interpolate_field(pts, vals, grid, method="idw", idw_neighbors=10)
+    assert np.allclose(U, 7.0, rtol=1e-12)
+    vals = rng.normal(size=(200, 3))
+    U, V, W = rp.interpolate_field(pts, vals, grid, method="idw", idw_neighbors=10)
+    assert abs(U[4, 4, 4] - vals[0, 0]) <= 1e-7 * max(1.0, abs(vals[0, 0]))
+    with pytest.raises(IndexError):
+        rp.interpolate_field(pts[:5], vals[:5], grid, method="idw", idw_neighbors=10)
+
+
+def test_reference_own_test_shape(golden_dir):
+    # test_parallel.py:27 only pins the output shape
+    g = _load(golden_dir, "case_e_test_parallel.npz")
+    assert g["uvw"].shape == (3, 10, 10, 10)
+    pts = np.array([[0, 0, 0], [10, 0, 0], [0, 10, 0], [10, 10, 0], [5, 5, 5]], dtype=float)
+    vals = np.array([[1, 0, 0], [1, 0, 0], [1, 0, 0], [1, 0, 0], [2, 0, 0]], dtype=float)
+    grid, _ = rp.create_grid(((0, 10), (0, 10), (0, 10)), 10)
+    U, V, W = rp.interpolate_field(pts, vals, grid, method="rbf")
+    assert np.array_equal(np.stack([U, V, W], 0), g["uvw"])
