@@ -1,0 +1,136 @@
+/*
+ * ptv_b200.h -- C ABI of the B200-native PTV scattered-to-grid interpolation path.
+ *
+ * The reference (tombultreys/ptv_interpolation) is pure Python and has no FFI: its boundary
+ * for this path is the module-level API of interpolator.py / physics.py.  Each entry point
+ * below names the reference interface it replaces (file:line in the upstream tree); the
+ * ctypes binding a maintainer would add is shown in INTEGRATION.md and shipped in
+ * ptv_interpolation_b200/_cabi.py.
+ *
+ * Conventions
+ *   - Every function returns a status (PTV_OK == 0).  On failure ptv_last_error() returns a
+ *     thread-local, NUL-terminated message.  The Python shim maps PTV_ERR_INVALID ->
+ *     ValueError, PTV_ERR_TOO_FEW -> IndexError (what interpolator.py:150 raises when
+ *     Np < k), PTV_ERR_SINGULAR -> numpy.linalg.LinAlgError (scipy _rbfinterp_np.py:74-87),
+ *     anything else -> RuntimeError.
+ *   - Pointers named d_* are DEVICE pointers (sm_100a, current device); h_* are HOST
+ *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Grids are (nz, ny, nx) C-ordered, x fastest, exactly as interpolator.py:59 builds them.
+ *     A mask byte != 0 means fluid/pore (interpolator.py:31-37).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     PTV_ERR_CUDA.
+ */
+#ifndef PTV_B200_H
+#define PTV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTV_OK 0
+#define PTV_ERR_INVALID 1
+#define PTV_ERR_TOO_FEW 2
+#define PTV_ERR_CUDA 3
+#define PTV_ERR_SINGULAR 4
+#define PTV_ERR_NOMEM 5
+
+/* interpolation methods (interpolator.py:65 `method=`) */
+#define PTV_METHOD_IDW 0     /* interpolator.py:126-155 */
+#define PTV_METHOD_SIBSON 1  /* interpolator.py:83-124  */
+#define PTV_METHOD_NEAREST 2 /* interpolator.py:197 griddata(method='nearest') == k=1 */
+#define PTV_METHOD_RBF 3     /* interpolator.py:157-195 local thin-plate-spline RBF */
+
+/* output element types for the velocity grids */
+#define PTV_F32 0
+#define PTV_F64 1
+
+typedef struct ptv_hash ptv_hash; /* opaque: uniform-grid cell list of the particle cloud */
+
+/* ---- library ------------------------------------------------------------------------- */
+int ptv_version(void);
+const char* ptv_last_error(void);
+/* sm count, compute capability and memory of `device`; fails with PTV_ERR_CUDA if absent. */
+int ptv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* Tuning knobs for experiments ("ppc" particles per cell, "r0" rings merged into the first
+ * staging batch, "tile" 64|128|256 threads per voxel tile).  Unknown key -> PTV_ERR_INVALID. */
+int ptv_set_tuning(const char* key, double value);
+/* Number of CUDA kernels this library has launched in this process so far (bench.py's
+ * gpu_launches is the difference across the timed region). */
+int64_t ptv_launch_count(void);
+double ptv_get_tuning(const char* key);
+
+/* ---- spatial hash: replaces KDTree(points) at interpolator.py:90,132 and the tree that
+ *      RBFInterpolator builds (scipy _rbfinterp.py:338) -------------------------------- */
+int ptv_hash_create(ptv_hash** out);
+int ptv_hash_destroy(ptv_hash* h);
+/* d_points: (n,3) float64 rows (x,y,z) == df[['x','y','z']].values (interpolator.py:78);
+ * d_values: (n,3) float64 rows (u,v,w) == df[['u','v','w']].values (interpolator.py:79).
+ * cell_size <= 0 picks the cell edge from the particle density.  Buffers owned by the
+ * handle are reused across builds (time-resolved sweeps rebuild per frame).            */
+int ptv_hash_build(ptv_hash* h, const double* d_points, const double* d_values, int64_t n,
+                   double cell_size, void* stream);
+int ptv_hash_info(const ptv_hash* h, int64_t* n, int dims[3], double origin[3], double* cell_size,
+                  int* max_cell_count);
+
+/* ---- fused kNN + weights + accumulate + mask: replaces tree.query + the NumPy weighting at
+ *      interpolator.py:97-122 / 139-153 and the solid zeroing at main.py:195-207 --------
+ * Queries are the rectilinear grid ax_x (x) ax_y (x) ax_z given by its three float64 axes
+ * (what create_grid returns as (x, y, z), interpolator.py:54-56).  d_mask may be NULL (all
+ * voxels interpolated, like the reference); with a mask, voxels whose byte is 0 are written
+ * as 0 and skipped.  d_knn_idx / d_knn_dist (nullable, (nvox,k), ascending by (d2, index))
+ * expose the neighbour lists for the bit-exact parity tests; solid voxels get -1 / NaN.  */
+int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, const double* d_ax_y, int ny,
+                   const double* d_ax_z, int nz, const uint8_t* d_mask, int method, int k,
+                   double idw_power, double rbf_smoothing, int out_dtype, void* d_u, void* d_v,
+                   void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream);
+
+/* ---- mask resampling: replaces sample_mask_on_grid (interpolator.py:205-238).  The
+ *      per-axis nearest index maps (-1 == out of bounds) are computed by the host shim with
+ *      the RegularGridInterpolator rule (scipy _rgi.py:551-554); this is the gather.     */
+int ptv_mask_gather(const uint8_t* d_mask_raw, int rnx, int rny, int rnz, const int32_t* d_ix,
+                    int nx, const int32_t* d_iy, int ny, const int32_t* d_iz, int nz,
+                    uint8_t* d_out, void* stream);
+
+/* ---- no-slip wall particles: replaces extract_boundary_particles (interpolator.py:240-284).
+ *      Flags solid voxels within `thickness` 6-connected dilation steps of fluid, compacts
+ *      their linear indices in C order into d_indices (capacity `cap`), total in *h_count. */
+int ptv_boundary_voxels(const uint8_t* d_mask, int nx, int ny, int nz, int thickness,
+                        int64_t* d_indices, int64_t cap, int64_t* h_count, void* stream);
+
+/* ---- solid zeroing alone (main.py:202-207) for fields produced elsewhere ---------------- */
+int ptv_apply_mask(void* d_u, void* d_v, void* d_w, const uint8_t* d_mask, int64_t nvox, int dtype,
+                   void* stream);
+
+/* ---- masked finite-volume divergence: replaces compute_consistent_divergence
+ *      (physics.py:6-53).  Slab form: planes [0,nz) of the local slab; d_w_below/d_w_above and
+ *      d_mask_above are the (ny,nx) halo planes from the z-neighbours, NULL at the domain
+ *      edge (Neumann, physics.py:38-45).  If d_absdiv_sum != NULL also accumulates
+ *      sum(|div|) over fluid voxels and their count into d_absdiv_sum[0..1] (float64,
+ *      physics.py:174).  dtype selects f32/f64 fields.                                    */
+int ptv_divergence(const void* d_u, const void* d_v, const void* d_w, const uint8_t* d_mask, int nx,
+                   int ny, int nz, double dx, double dy, double dz, const void* d_w_below,
+                   const void* d_w_above, const uint8_t* d_mask_above, int dtype, void* d_div,
+                   double* d_absdiv_sum, void* stream);
+
+/* ---- plane fluxes: replaces calculate_flux_xy/xz/yz (plot_flux.py:6-16) and the mid-plane
+ *      X flux (physics.py:160-165).  Outputs are float64 sums WITHOUT the dx*dy area factor
+ *      (the shim multiplies, as the reference does after np.sum): d_qxy[nz], d_qxz[ny],
+ *      d_qyz[nx] must be zeroed by the caller (the kernel accumulates, so slabs can share). */
+int ptv_flux_profiles(const void* d_u, const void* d_v, const void* d_w, int nx, int ny, int nz,
+                      int dtype, double* d_qxy, double* d_qxz, double* d_qyz, void* stream);
+
+/* ---- host-buffer convenience (what a non-CUDA caller binds): copies in, runs
+ *      ptv_hash_build + ptv_knn_interp, copies out.  All pointers are HOST pointers. ------ */
+int ptv_interpolate_host(const double* h_points, const double* h_values, int64_t n,
+                         const double* h_ax_x, int nx, const double* h_ax_y, int ny,
+                         const double* h_ax_z, int nz, const uint8_t* h_mask, int method, int k,
+                         double idw_power, double rbf_smoothing, int out_dtype, void* h_u, void* h_v,
+                         void* h_w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTV_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of libptvb200.so (the C ABI declared in include/ptv_b200.h).
+
+This is the stub a maintainer of the reference would add.  There is no CPU
+fallback: if the shared library is missing and cannot be built, or no CUDA device is present,
+every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PTV_OK, PTV_ERR_INVALID, PTV_ERR_TOO_FEW, PTV_ERR_CUDA, PTV_ERR_SINGULAR, PTV_ERR_NOMEM = range(6)
+METHOD_IDW, METHOD_SIBSON, METHOD_NEAREST, METHOD_RBF = range(4)
+F32, F64 = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libptvb200.so")
+_lib = None
+
+EXPORTS = [
+    "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
+    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp",
+    "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence",
+    "ptv_flux_profiles", "ptv_interpolate_host",
+]
+
+
+class PTVError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    lib.ptv_version.restype = i32
+    lib.ptv_version.argtypes = []
+    lib.ptv_last_error.restype = C.c_char_p
+    lib.ptv_last_error.argtypes = []
+    lib.ptv_device_info.restype = i32
+    lib.ptv_device_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_size_t)]
+    lib.ptv_set_tuning.restype = i32
+    lib.ptv_set_tuning.argtypes = [C.c_char_p, f64]
+    lib.ptv_get_tuning.restype = f64
+    lib.ptv_get_tuning.argtypes = [C.c_char_p]
+    lib.ptv_launch_count.restype = i64
+    lib.ptv_launch_count.argtypes = []
+    lib.ptv_hash_create.restype = i32
+    lib.ptv_hash_create.argtypes = [C.POINTER(vp)]
+    lib.ptv_hash_destroy.restype = i32
+    lib.ptv_hash_destroy.argtypes = [vp]
+    lib.ptv_hash_build.restype = i32
+    lib.ptv_hash_build.argtypes = [vp, vp, vp, i64, f64, vp]
+    lib.ptv_hash_info.restype = i32
+    lib.ptv_hash_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32 * 3), C.POINTER(f64 * 3), C.POINTER(f64),
+                                  C.POINTER(i32)]
+    lib.ptv_knn_interp.restype = i32
+    lib.ptv_knn_interp.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp, vp]
+    lib.ptv_mask_gather.restype = i32
+    lib.ptv_mask_gather.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
+    lib.ptv_boundary_voxels.restype = i32
+    lib.ptv_boundary_voxels.argtypes = [vp, i32, i32, i32, i32, vp, i64, C.POINTER(i64), vp]
+    lib.ptv_apply_mask.restype = i32
+    lib.ptv_apply_mask.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    lib.ptv_divergence.restype = i32
+    lib.ptv_divergence.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, vp, vp, vp, i32, vp, vp, vp]
+    lib.ptv_flux_profiles.restype = i32
+    lib.ptv_flux_profiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.ptv_interpolate_host.restype = i32
+    lib.ptv_interpolate_host.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp, i32, vp, i32, i32, f64, f64, i32,
+                                         vp, vp, vp]
+
+
+def load():
+    """Load (building in-tree first if needed) the shared library; raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    """Map a C status to the exception type the reference raises in the same situation."""
+    if rc == PTV_OK:
+        return
+    msg = load().ptv_last_error().decode("utf-8", "replace")
+    if rc == PTV_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == PTV_ERR_TOO_FEW:
+        raise IndexError(msg)
+    if rc == PTV_ERR_SINGULAR:
+        raise np.linalg.LinAlgError(msg)
+    if rc == PTV_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise PTVError(msg)

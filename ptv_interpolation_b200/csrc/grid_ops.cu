@@ -1,0 +1,438 @@
+// HBM-bound grid kernels that sit either side of the interpolation: mask resampling gather,
+// no-slip boundary-voxel extraction, solid zeroing, the masked finite-volume divergence stencil
+// and the plane-flux / mean|div| reductions.  Each is a single streaming pass; the algorithmic
+// bytes per voxel are listed in DESIGN.md.
+#include <math.h>
+
+#include "ptv_internal.cuh"
+
+namespace ptv {
+
+// ------------------------------------------------------------------ mask gather (a2)
+// out[z,y,x] = raw[iz[z], iy[y], ix[x]] != 0, 0 where any index is -1 (out of bounds ->
+// fill_value 0, interpolator.py:230-231).  One thread = 4 consecutive x.
+__global__ void __launch_bounds__(256) mask_gather_kernel(const uint8_t* __restrict__ raw, int rnx, int rny,
+                                                           const int32_t* __restrict__ mx,
+                                                           const int32_t* __restrict__ my,
+                                                           const int32_t* __restrict__ mz, int nx, int ny,
+                                                           int nz, uint8_t* __restrict__ out) {
+  const int gx = (nx + 3) >> 2;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)gx * ny * nz;
+  if (gid >= total) return;
+  const int xg = (int)(gid % gx);
+  const int64_t row = gid / gx;
+  const int y = (int)(row % ny), z = (int)(row / ny);
+  const int sz = mz[z], sy = my[y];
+  const bool rowok = sz >= 0 && sy >= 0;
+  const uint8_t* src = raw + ((int64_t)(rowok ? sz : 0) * rny + (rowok ? sy : 0)) * rnx;
+  uint8_t v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = xg * 4 + j;
+    uint8_t r = 0;
+    if (x < nx && rowok) {
+      const int sx = mx[x];
+      if (sx >= 0) r = src[sx] != 0 ? 1 : 0;
+    }
+    v[j] = r;
+  }
+  uint8_t* dst = out + row * nx + (int64_t)xg * 4;
+  if ((nx & 3) == 0 && ((uintptr_t)out & 3) == 0) {
+    *reinterpret_cast<uchar4*>(dst) = make_uchar4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (xg * 4 + j < nx) dst[j] = v[j];
+  }
+}
+
+// ------------------------------------------------------------------ boundary voxels (a3)
+// One 6-connected dilation step with border_value = 0 (scipy.ndimage.binary_dilation).
+__global__ void __launch_bounds__(256) dilate6_kernel(const uint8_t* __restrict__ in, int nx, int ny, int nz,
+                                                       uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = (int64_t)nx * ny * nz;
+  if (i >= n) return;
+  const int x = (int)(i % nx);
+  const int y = (int)((i / nx) % ny);
+  const int z = (int)(i / ((int64_t)nx * ny));
+  const int64_t sy = nx, sz = (int64_t)nx * ny;
+  uint8_t r = in[i] != 0;
+  if (!r) {
+    r = (x > 0 && in[i - 1]) || (x + 1 < nx && in[i + 1]) || (y > 0 && in[i - sy]) ||
+        (y + 1 < ny && in[i + sy]) || (z > 0 && in[i - sz]) || (z + 1 < nz && in[i + sz]);
+  }
+  out[i] = r;
+}
+
+static constexpr int kCompThreads = 256;
+static constexpr int kCompItems = 8;
+static constexpr int kCompTile = kCompThreads * kCompItems;
+
+__device__ __forceinline__ int comp_block_scan(int v, int* total_out) {
+  __shared__ int warp_tot[kCompThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  int woff = 0, tot = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < kCompThreads / 32; ++w2) {
+    int t = warp_tot[w2];
+    if (w2 < wid) woff += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total_out = tot;
+  return woff + inc - v;
+}
+
+// flag = dilated & !mask.  pass 0: per-tile counts; pass 1: ordered (C order) index write.
+template <int PASS>
+__global__ void __launch_bounds__(kCompThreads) boundary_compact_kernel(
+    const uint8_t* __restrict__ dil, const uint8_t* __restrict__ mask, int64_t n,
+    int64_t* __restrict__ tile_counts, const int64_t* __restrict__ tile_offsets,
+    int64_t* __restrict__ indices, int64_t cap) {
+  const int64_t base = (int64_t)blockIdx.x * kCompTile + (int64_t)threadIdx.x * kCompItems;
+  int flags = 0, c = 0;
+#pragma unroll
+  for (int j = 0; j < kCompItems; ++j) {
+    const int64_t i = base + j;
+    if (i < n && dil[i] != 0 && mask[i] == 0) {
+      flags |= 1 << j;
+      ++c;
+    }
+  }
+  int tot;
+  const int ex = comp_block_scan(c, &tot);
+  if (PASS == 0) {
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
+  } else {
+    int64_t o = tile_offsets[blockIdx.x] + ex;
+#pragma unroll
+    for (int j = 0; j < kCompItems; ++j) {
+      if (flags & (1 << j)) {
+        if (o < cap) indices[o] = base + j;
+        ++o;
+      }
+    }
+  }
+}
+
+// exclusive scan of int64 tile counts by one block (tile count = nvox/2048 <= ~0.5M at 1024^3)
+__global__ void __launch_bounds__(1024) scan_i64_kernel(const int64_t* __restrict__ in, int64_t n,
+                                                         int64_t* __restrict__ out, int64_t* __restrict__ total) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int64_t v = i < n ? in[i] : 0;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int64_t woff = 0, tot = 0;
+    for (int w2 = 0; w2 < 32; ++w2) {
+      const int64_t t = warp_tot[w2];
+      if (w2 < wid) woff += t;
+      tot += t;
+    }
+    const int64_t carry = carry_s;
+    if (i < n) out[i] = carry + woff + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
+// ------------------------------------------------------------------ solid zeroing (a11)
+template <typename Tf>
+__global__ void __launch_bounds__(256) apply_mask_kernel(Tf* __restrict__ u, Tf* __restrict__ v, Tf* __restrict__ w,
+                                                          const uint8_t* __restrict__ mask, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // main.py:195-207: NaN -> 0, then zero where the mask is solid
+  const bool solid = mask != nullptr && mask[i] == 0;
+  Tf a = u[i], b = v[i], c = w[i];
+  if (solid || a != a) u[i] = (Tf)0;
+  if (solid || b != b) v[i] = (Tf)0;
+  if (solid || c != c) w[i] = (Tf)0;
+}
+
+// ------------------------------------------------------------------ divergence (a12)
+// Closed form of physics.py:26-53, evaluated in float64 with the reference's
+// operation order and no FMA contraction, so float64 fields reproduce NumPy bit for bit:
+//   F+ = i == n-1 ? f[i] : (m[i+1] ? (f[i] + f[i+1]) / 2 : 0)
+//   F- = i == 0   ? f[0] : (m[i]   ? (f[i-1] + f[i]) / 2 : 0)
+//   div = ((F+x - F-x)/dx + (F+y - F-y)/dy) + (F+z - F-z)/dz
+template <typename Tf>
+__global__ void __launch_bounds__(256) divergence_kernel(
+    const Tf* __restrict__ u, const Tf* __restrict__ v, const Tf* __restrict__ w,
+    const uint8_t* __restrict__ mask, int nx, int ny, int nz, double dx, double dy, double dz,
+    const Tf* __restrict__ w_below, const Tf* __restrict__ w_above, const uint8_t* __restrict__ mask_above,
+    Tf* __restrict__ div, double* __restrict__ absdiv_sum) {
+  const int64_t n = (int64_t)nx * ny * nz;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double absval = 0.0, cnt = 0.0;
+  if (i < n) {
+    const int x = (int)(i % nx);
+    const int y = (int)((i / nx) % ny);
+    const int z = (int)(i / ((int64_t)nx * ny));
+    const int64_t sy = nx, sz = (int64_t)nx * ny;
+    const bool m = mask[i] != 0;
+    // x (u, axis 2)
+    const double uc = (double)u[i];
+    double fp, fm;
+    if (x == nx - 1) fp = uc;
+    else fp = mask[i + 1] ? __ddiv_rn(__dadd_rn(uc, (double)u[i + 1]), 2.0) : 0.0;
+    if (x == 0) fm = uc;
+    else fm = m ? __ddiv_rn(__dadd_rn((double)u[i - 1], uc), 2.0) : 0.0;
+    const double tx = __ddiv_rn(__dsub_rn(fp, fm), dx);
+    // y (v, axis 1)
+    const double vc = (double)v[i];
+    if (y == ny - 1) fp = vc;
+    else fp = mask[i + sy] ? __ddiv_rn(__dadd_rn(vc, (double)v[i + sy]), 2.0) : 0.0;
+    if (y == 0) fm = vc;
+    else fm = m ? __ddiv_rn(__dadd_rn((double)v[i - sy], vc), 2.0) : 0.0;
+    const double ty = __ddiv_rn(__dsub_rn(fp, fm), dy);
+    // z (w, axis 0) -- slab halos stand in for the planes owned by the z-neighbours
+    const double wc = (double)w[i];
+    const int64_t pl = (int64_t)y * nx + x;
+    if (z == nz - 1) {
+      if (w_above != nullptr) fp = mask_above[pl] ? __ddiv_rn(__dadd_rn(wc, (double)w_above[pl]), 2.0) : 0.0;
+      else fp = wc;
+    } else {
+      fp = mask[i + sz] ? __ddiv_rn(__dadd_rn(wc, (double)w[i + sz]), 2.0) : 0.0;
+    }
+    if (z == 0) {
+      if (w_below != nullptr) fm = m ? __ddiv_rn(__dadd_rn((double)w_below[pl], wc), 2.0) : 0.0;
+      else fm = wc;
+    } else {
+      fm = m ? __ddiv_rn(__dadd_rn((double)w[i - sz], wc), 2.0) : 0.0;
+    }
+    const double tz = __ddiv_rn(__dsub_rn(fp, fm), dz);
+    const double d = __dadd_rn(__dadd_rn(tx, ty), tz);
+    div[i] = (Tf)d;
+    if (m) {
+      absval = fabs((double)(Tf)d);
+      cnt = 1.0;
+    }
+  }
+  if (absdiv_sum != nullptr) {  // uniform branch: block reduction then one atomic pair per block
+    __shared__ double sh[2][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      absval += __shfl_xor_sync(0xffffffffu, absval, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wid] = absval; sh[1][wid] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, c = 0.0;
+      for (int w2 = 0; w2 < 8; ++w2) { a += sh[0][w2]; c += sh[1][w2]; }
+      if (c > 0.0) {
+        atomicAdd(&absdiv_sum[0], a);
+        atomicAdd(&absdiv_sum[1], c);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ flux profiles (a13)
+// q_xy[z] += sum_{y,x} w   (plot_flux.py:6-8)
+template <typename Tf>
+__global__ void __launch_bounds__(256) flux_xy_kernel(const Tf* __restrict__ w, int64_t plane, int chunks,
+                                                       double* __restrict__ qxy) {
+  const int z = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+  const int64_t per = (plane + chunks - 1) / chunks;
+  const int64_t lo = (int64_t)ch * per, hi = min(plane, lo + per);
+  const Tf* src = w + (int64_t)z * plane;
+  double acc = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) acc += (double)src[i];
+  __shared__ double sh[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w2 = 0; w2 < 8; ++w2) a += sh[w2];
+    atomicAdd(&qxy[z], a);
+  }
+}
+
+// q_xz[y] += sum_{z,x} v   (plot_flux.py:10-12): one warp per (z, y) row
+template <typename Tf>
+__global__ void __launch_bounds__(256) flux_xz_kernel(const Tf* __restrict__ v, int nx, int ny, int nz,
+                                                       double* __restrict__ qxz) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (int64_t)ny * nz) return;
+  const int y = (int)(row % ny);
+  const Tf* src = v + row * nx;
+  double acc = 0.0;
+  for (int x = threadIdx.x & 31; x < nx; x += 32) acc += (double)src[x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&qxz[y], acc);
+}
+
+// q_yz[x] += sum_{z,y} u   (plot_flux.py:14-16): one thread per x, marching over y of one plane
+template <typename Tf>
+__global__ void __launch_bounds__(256) flux_yz_kernel(const Tf* __restrict__ u, int nx, int ny,
+                                                       double* __restrict__ qyz) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  const int z = blockIdx.y;
+  if (x >= nx) return;
+  const Tf* src = u + (int64_t)z * ny * nx + x;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int y = 0;
+  for (; y + 3 < ny; y += 4) {
+    a0 += (double)src[(int64_t)y * nx];
+    a1 += (double)src[(int64_t)(y + 1) * nx];
+    a2 += (double)src[(int64_t)(y + 2) * nx];
+    a3 += (double)src[(int64_t)(y + 3) * nx];
+  }
+  for (; y < ny; ++y) a0 += (double)src[(int64_t)y * nx];
+  atomicAdd(&qyz[x], (a0 + a1) + (a2 + a3));
+}
+
+}  // namespace ptv
+
+using namespace ptv;
+
+extern "C" int ptv_mask_gather(const uint8_t* d_mask_raw, int rnx, int rny, int rnz, const int32_t* d_ix, int nx,
+                               const int32_t* d_iy, int ny, const int32_t* d_iz, int nz, uint8_t* d_out,
+                               void* stream) {
+  if (!d_mask_raw || !d_ix || !d_iy || !d_iz || !d_out) { set_error("ptv_mask_gather: NULL argument"); return PTV_ERR_INVALID; }
+  if (rnx <= 0 || rny <= 0 || rnz <= 0 || nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_mask_gather: empty array"); return PTV_ERR_INVALID; }
+  const int64_t total = (int64_t)((nx + 3) / 4) * ny * nz;
+  mask_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_mask_raw, rnx, rny, d_ix, d_iy, d_iz, nx, ny, nz, d_out);
+  count_launches(1);
+  PTV_CUDA(cudaGetLastError());
+  return PTV_OK;
+}
+
+extern "C" int ptv_boundary_voxels(const uint8_t* d_mask, int nx, int ny, int nz, int thickness,
+                                   int64_t* d_indices, int64_t cap, int64_t* h_count, void* stream_) {
+  if (!d_mask || !h_count) { set_error("ptv_boundary_voxels: NULL argument"); return PTV_ERR_INVALID; }
+  if (nx <= 0 || ny <= 0 || nz <= 0 || thickness < 0) { set_error("ptv_boundary_voxels: bad shape/thickness"); return PTV_ERR_INVALID; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t n = (int64_t)nx * ny * nz;
+  const int64_t ntiles = (n + kCompTile - 1) / kCompTile;
+  uint8_t *a = nullptr, *b = nullptr;
+  int64_t* counts = nullptr;
+  cudaError_t e = cudaMalloc(&a, (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc(&b, (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc(&counts, (size_t)(2 * ntiles + 1) * sizeof(int64_t));
+  int rc = PTV_OK;
+  if (e != cudaSuccess) rc = cuda_fail(e, "ptv_boundary_voxels alloc", __FILE__, __LINE__);
+  if (rc == PTV_OK) {
+    const uint8_t* cur = d_mask;
+    uint8_t* bufs[2] = {a, b};
+    for (int it = 0; it < thickness; ++it) {
+      uint8_t* dst = bufs[it & 1];
+      dilate6_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cur, nx, ny, nz, dst);
+      cur = dst;
+    }
+    count_launches(thickness + 2 + ((d_indices != nullptr && cap > 0) ? 1 : 0));
+    int64_t* offsets = counts + ntiles;
+    boundary_compact_kernel<0><<<(unsigned)ntiles, kCompThreads, 0, stream>>>(cur, d_mask, n, counts, nullptr, nullptr, 0);
+    scan_i64_kernel<<<1, 1024, 0, stream>>>(counts, ntiles, offsets, offsets + ntiles);
+    if (d_indices != nullptr && cap > 0)
+      boundary_compact_kernel<1><<<(unsigned)ntiles, kCompThreads, 0, stream>>>(cur, d_mask, n, nullptr, offsets, d_indices, cap);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_count, offsets + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "ptv_boundary_voxels", __FILE__, __LINE__);
+  }
+  cudaFree(a); cudaFree(b); cudaFree(counts);
+  return rc;
+}
+
+extern "C" int ptv_apply_mask(void* d_u, void* d_v, void* d_w, const uint8_t* d_mask, int64_t nvox, int dtype,
+                              void* stream) {
+  if (!d_u || !d_v || !d_w) { set_error("ptv_apply_mask: NULL argument"); return PTV_ERR_INVALID; }
+  if (nvox <= 0) return PTV_OK;
+  const unsigned nb = (unsigned)((nvox + 255) / 256);
+  if (dtype == PTV_F32)
+    apply_mask_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>((float*)d_u, (float*)d_v, (float*)d_w, d_mask, nvox);
+  else if (dtype == PTV_F64)
+    apply_mask_kernel<double><<<nb, 256, 0, (cudaStream_t)stream>>>((double*)d_u, (double*)d_v, (double*)d_w, d_mask, nvox);
+  else { set_error("ptv_apply_mask: bad dtype"); return PTV_ERR_INVALID; }
+  count_launches(1);
+  PTV_CUDA(cudaGetLastError());
+  return PTV_OK;
+}
+
+extern "C" int ptv_divergence(const void* d_u, const void* d_v, const void* d_w, const uint8_t* d_mask, int nx,
+                              int ny, int nz, double dx, double dy, double dz, const void* d_w_below,
+                              const void* d_w_above, const uint8_t* d_mask_above, int dtype, void* d_div,
+                              double* d_absdiv_sum, void* stream) {
+  if (!d_u || !d_v || !d_w || !d_mask || !d_div) { set_error("ptv_divergence: NULL argument"); return PTV_ERR_INVALID; }
+  if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_divergence: empty grid"); return PTV_ERR_INVALID; }
+  if ((d_w_above == nullptr) != (d_mask_above == nullptr)) { set_error("ptv_divergence: w_above and mask_above go together"); return PTV_ERR_INVALID; }
+  const int64_t n = (int64_t)nx * ny * nz;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (dtype == PTV_F32)
+    divergence_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dx, dy, dz,
+        (const float*)d_w_below, (const float*)d_w_above, d_mask_above, (float*)d_div, d_absdiv_sum);
+  else if (dtype == PTV_F64)
+    divergence_kernel<double><<<nb, 256, 0, (cudaStream_t)stream>>>(
+        (const double*)d_u, (const double*)d_v, (const double*)d_w, d_mask, nx, ny, nz, dx, dy, dz,
+        (const double*)d_w_below, (const double*)d_w_above, d_mask_above, (double*)d_div, d_absdiv_sum);
+  else { set_error("ptv_divergence: bad dtype"); return PTV_ERR_INVALID; }
+  count_launches(1);
+  PTV_CUDA(cudaGetLastError());
+  return PTV_OK;
+}
+
+template <typename Tf>
+static int flux_launch(const void* u, const void* v, const void* w, int nx, int ny, int nz, double* qxy,
+                       double* qxz, double* qyz, cudaStream_t s) {
+  const int64_t plane = (int64_t)nx * ny;
+  if (w && qxy) {
+    int chunks = (int)((plane + 65535) / 65536);
+    if (chunks < 1) chunks = 1;
+    flux_xy_kernel<Tf><<<(unsigned)(nz * chunks), 256, 0, s>>>((const Tf*)w, plane, chunks, qxy);
+    count_launches(1);
+  }
+  if (v && qxz) {
+    const int64_t rows = (int64_t)ny * nz;
+    flux_xz_kernel<Tf><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const Tf*)v, nx, ny, nz, qxz);
+    count_launches(1);
+  }
+  if (u && qyz) {
+    dim3 grid((unsigned)((nx + 255) / 256), (unsigned)nz);
+    flux_yz_kernel<Tf><<<grid, 256, 0, s>>>((const Tf*)u, nx, ny, qyz);
+    count_launches(1);
+  }
+  PTV_CUDA(cudaGetLastError());
+  return PTV_OK;
+}
+
+extern "C" int ptv_flux_profiles(const void* d_u, const void* d_v, const void* d_w, int nx, int ny, int nz,
+                                 int dtype, double* d_qxy, double* d_qxz, double* d_qyz, void* stream) {
+  if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_flux_profiles: empty grid"); return PTV_ERR_INVALID; }
+  if (nz > 65535) { set_error("ptv_flux_profiles: nz > 65535 planes per call"); return PTV_ERR_INVALID; }
+  if (dtype == PTV_F32) return flux_launch<float>(d_u, d_v, d_w, nx, ny, nz, d_qxy, d_qxz, d_qyz, (cudaStream_t)stream);
+  if (dtype == PTV_F64) return flux_launch<double>(d_u, d_v, d_w, nx, ny, nz, d_qxy, d_qxz, d_qyz, (cudaStream_t)stream);
+  set_error("ptv_flux_profiles: bad dtype");
+  return PTV_ERR_INVALID;
+}

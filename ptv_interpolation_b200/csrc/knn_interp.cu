@@ -1,0 +1,475 @@
+// Fused kNN search + weights + accumulate + solid zeroing (replaces tree.query and the NumPy
+// weighting at interpolator.py:97-122 / 139-153 and main.py:195-207).
+//
+// Mapping: one CTA = one TX x TY x TZ tile of voxels, one thread = one voxel.  The tile walks the
+// particle cell list ring by ring outwards from its own cells; each ring's cell rows are
+// contiguous ranges of 32-byte particle records that the CTA stages through shared memory and
+// every thread scans (broadcast reads).  Each thread keeps its k best (d2, index) pairs in a
+// shared-memory max-heap laid out [slot][thread] (bank-conflict free for any per-thread slot),
+// with the current k-th distance in a register so most candidates are rejected with one compare.
+// The search stops when every voxel's k-th distance is inside the scanned box (exact test).
+//
+// Exactness: d2 = (dx*dx + dy*dy) + dz*dz in float64 with no FMA contraction, ordering is
+// (d2, original index) -- the same total order as the canonicalised oracle -- so the selected
+// neighbour SET and its sorted order are bit-exact regardless of staging order.
+#include <math.h>
+
+#include "ptv_internal.cuh"
+
+namespace ptv {
+
+static constexpr int kStageCap = 256;  // particle records per staging chunk (8 KB)
+
+struct KnnParams {
+  HashGrid g;
+  const double* ax;
+  const double* ay;
+  const double* az;
+  int nx, ny, nz;
+  const uint8_t* mask;
+  int method;
+  int k;
+  double power;
+  void* u;
+  void* v;
+  void* w;
+  int64_t* knn_idx;
+  double* knn_dist;
+  int tiles_x, tiles_y, tiles_z;
+  int r0;
+};
+
+__device__ __forceinline__ bool key_greater(double ka, int ia, double kb, int ib) {
+  return ka > kb || (ka == kb && ia > ib);
+}
+
+// Place (nk, ni) at `pos` of the size-n max-heap and sift it down.  Column `t` of [slot][T].
+template <int T>
+__device__ __forceinline__ void sift_down(double* __restrict__ hk, int* __restrict__ hi, int n, int pos,
+                                          double nk, int ni) {
+  for (;;) {
+    int c = 2 * pos + 1;
+    if (c >= n) break;
+    double kc = hk[c * T];
+    int ic = hi[c * T];
+    if (c + 1 < n) {
+      const double kr = hk[(c + 1) * T];
+      const int ir = hi[(c + 1) * T];
+      if (key_greater(kr, ir, kc, ic)) {
+        kc = kr;
+        ic = ir;
+        c = c + 1;
+      }
+    }
+    if (!key_greater(kc, ic, nk, ni)) break;
+    hk[pos * T] = kc;
+    hi[pos * T] = ic;
+    pos = c;
+  }
+  hk[pos * T] = nk;
+  hi[pos * T] = ni;
+}
+
+template <int T>
+__device__ __forceinline__ int block_scan_excl(int v, int* warp_tot, int* total) {
+  constexpr int NW = T / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  int woff = 0, tot = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < NW; ++w2) {
+    const int x = warp_tot[w2];
+    if (w2 < wid) woff += x;
+    tot += x;
+  }
+  __syncthreads();
+  *total = tot;
+  return woff + inc - v;
+}
+
+__device__ __forceinline__ int cell_of(double p, double o, double inv_cell, int n) {
+  const int c = (int)floor((p - o) * inv_cell);
+  return min(max(c, 0), n - 1);
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_out(void* base, int64_t i, double v) {
+  reinterpret_cast<OutT*>(base)[i] = (OutT)v;
+}
+
+template <int T, int TX, int TY, int TZ, typename OutT>
+__global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
+  static_assert(TX * TY * TZ == T, "tile shape");
+  constexpr int NW = T / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int k = p.k;
+  double* hkey_all = reinterpret_cast<double*>(smem_raw);               // [k][T]
+  ParticleRec* stage = reinterpret_cast<ParticleRec*>(hkey_all + (size_t)k * T);  // [kStageCap]
+  double* red = reinterpret_cast<double*>(stage + kStageCap);           // [6][NW]
+  int* hidx_all = reinterpret_cast<int*>(red + 6 * NW);                 // [k][T]
+  int* seg_start = hidx_all + (size_t)k * T;                            // [T]
+  int* seg_off = seg_start + T;                                         // [T+1]
+  int* warp_tot = seg_off + T + 1;                                      // [NW]
+
+  const int t = threadIdx.x;
+  double* hk = hkey_all + t;
+  int* hi = hidx_all + t;
+
+  const HashGrid& g = p.g;
+  const int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x;
+  const int ty = (tile / p.tiles_x) % p.tiles_y;
+  const int tz = tile / (p.tiles_x * p.tiles_y);
+  const int ix = tx * TX + (t % TX);
+  const int iy = ty * TY + ((t / TX) % TY);
+  const int iz = tz * TZ + (t / (TX * TY));
+  const bool valid = ix < p.nx && iy < p.ny && iz < p.nz;
+  const int64_t vox = valid ? ((int64_t)iz * p.ny + iy) * p.nx + ix : 0;
+  const bool active = valid && (p.mask == nullptr || p.mask[vox] != 0);
+
+  if (!__syncthreads_or(active ? 1 : 0)) {  // tile entirely solid / outside: zero fill
+    if (valid) {
+      store_out<OutT>(p.u, vox, 0.0);
+      store_out<OutT>(p.v, vox, 0.0);
+      store_out<OutT>(p.w, vox, 0.0);
+      if (p.knn_idx) {
+        for (int j = 0; j < k; ++j) {
+          p.knn_idx[vox * k + j] = -1;
+          p.knn_dist[vox * k + j] = nan("");
+        }
+      }
+    }
+    return;
+  }
+
+  const double qx = valid ? p.ax[ix] : 0.0;
+  const double qy = valid ? p.ay[iy] : 0.0;
+  const double qz = valid ? p.az[iz] : 0.0;
+
+  // ---- bounding box of the tile's active voxels -> cell range of ring 0
+  {
+    double v6[6];
+    v6[0] = active ? qx : INFINITY;
+    v6[1] = active ? qy : INFINITY;
+    v6[2] = active ? qz : INFINITY;
+    v6[3] = active ? -qx : INFINITY;
+    v6[4] = active ? -qy : INFINITY;
+    v6[5] = active ? -qz : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v6[c] = fmin(v6[c], __shfl_xor_sync(0xffffffffu, v6[c], o));
+    }
+    if ((t & 31) == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) red[c * NW + (t >> 5)] = v6[c];
+    }
+  }
+  __syncthreads();
+  double bb[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double a = red[c * NW];
+#pragma unroll
+    for (int w2 = 1; w2 < NW; ++w2) a = fmin(a, red[c * NW + w2]);
+    bb[c] = a;
+  }
+  const int c0x = cell_of(bb[0], g.ox, g.inv_cell, g.cnx);
+  const int c0y = cell_of(bb[1], g.oy, g.inv_cell, g.cny);
+  const int c0z = cell_of(bb[2], g.oz, g.inv_cell, g.cnz);
+  const int c1x = cell_of(-bb[3], g.ox, g.inv_cell, g.cnx);
+  const int c1y = cell_of(-bb[4], g.oy, g.inv_cell, g.cny);
+  const int c1z = cell_of(-bb[5], g.oz, g.inv_cell, g.cnz);
+
+  int count = 0;
+  double thr = INFINITY;  // k-th best d2 once the heap is full
+  int root_idx = 0x7fffffff;
+
+  bool have_prev = false;
+  int pbx0 = 0, pbx1 = -1, pby0 = 0, pby1 = -1, pbz0 = 0, pbz1 = -1;
+  int r = p.r0;
+  for (;;) {
+    const int bx0 = max(c0x - r, 0), bx1 = min(c1x + r, g.cnx - 1);
+    const int by0 = max(c0y - r, 0), by1 = min(c1y + r, g.cny - 1);
+    const int bz0 = max(c0z - r, 0), bz1 = min(c1z + r, g.cnz - 1);
+    if (have_prev && bx0 == pbx0 && bx1 == pbx1 && by0 == pby0 && by1 == pby1 && bz0 == pbz0 &&
+        bz1 == pbz1)
+      break;  // the whole cell grid has been scanned
+    const int nrows_y = by1 - by0 + 1;
+    const int nrows = nrows_y * (bz1 - bz0 + 1);
+    const int nslots = have_prev ? 2 * nrows : nrows;
+
+    for (int slot_base = 0; slot_base < nslots; slot_base += T) {
+      // ---- each thread resolves one row segment of the shell to a contiguous record range
+      const int s = slot_base + t;
+      int start = 0, cnt = 0;
+      if (s < nslots) {
+        const int row = have_prev ? (s >> 1) : s;
+        const int which = have_prev ? (s & 1) : 0;
+        const int cy = by0 + row % nrows_y;
+        const int cz = bz0 + row / nrows_y;
+        int xa, xb;  // inclusive cell range along x
+        if (!have_prev || cy < pby0 || cy > pby1 || cz < pbz0 || cz > pbz1) {
+          xa = which == 0 ? bx0 : 1;
+          xb = which == 0 ? bx1 : 0;
+        } else if (which == 0) {
+          xa = bx0;
+          xb = pbx0 - 1;
+        } else {
+          xa = pbx1 + 1;
+          xb = bx1;
+        }
+        if (xa <= xb) {
+          const int64_t rowbase = ((int64_t)cz * g.cny + cy) * g.cnx;
+          start = g.cell_start[rowbase + xa];
+          cnt = g.cell_start[rowbase + xb + 1] - start;
+        }
+      }
+      int total;
+      const int off = block_scan_excl<T>(cnt, warp_tot, &total);
+      seg_start[t] = start;
+      seg_off[t] = off;
+      if (t == 0) seg_off[T] = total;
+      __syncthreads();
+
+      for (int chunk0 = 0; chunk0 < total; chunk0 += kStageCap) {
+        const int m = min(kStageCap, total - chunk0);
+        // ---- stage: record j of the chunk lives in the last segment whose offset <= j
+        for (int j = t; j < m; j += T) {
+          const int gpos = chunk0 + j;
+          int lo = 0, hi2 = T - 1;
+          while (lo < hi2) {
+            const int mid = (lo + hi2 + 1) >> 1;
+            if (seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
+          }
+          const int4* src = reinterpret_cast<const int4*>(g.rec + (seg_start[lo] + (gpos - seg_off[lo])));
+          int4* dst = reinterpret_cast<int4*>(stage + j);
+          dst[0] = __ldg(src);
+          dst[1] = __ldg(src + 1);
+        }
+        __syncthreads();
+        // ---- scan: every active thread tests every staged particle
+        if (active) {
+#pragma unroll 2
+          for (int j = 0; j < m; ++j) {
+            const double2 xy = *reinterpret_cast<const double2*>(&stage[j].x);
+            const double zz = stage[j].z;
+            const int pidx = stage[j].idx;
+            const double dx = qx - xy.x, dy = qy - xy.y, dz = qz - zz;
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d2 < thr || (d2 == thr && pidx < root_idx)) {
+              if (count < k) {
+                hk[count * T] = d2;
+                hi[count * T] = pidx;
+                ++count;
+                if (count == k) {
+                  for (int h = k / 2 - 1; h >= 0; --h) sift_down<T>(hk, hi, k, h, hk[h * T], hi[h * T]);
+                  thr = hk[0];
+                  root_idx = hi[0];
+                }
+              } else {
+                sift_down<T>(hk, hi, k, 0, d2, pidx);
+                thr = hk[0];
+                root_idx = hi[0];
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- exact termination: the k-th distance must be inside the scanned box
+    double gap = INFINITY;
+    if (bx0 > 0) gap = fmin(gap, qx - (g.ox + bx0 * g.cell));
+    if (bx1 < g.cnx - 1) gap = fmin(gap, (g.ox + (bx1 + 1) * g.cell) - qx);
+    if (by0 > 0) gap = fmin(gap, qy - (g.oy + by0 * g.cell));
+    if (by1 < g.cny - 1) gap = fmin(gap, (g.oy + (by1 + 1) * g.cell) - qy);
+    if (bz0 > 0) gap = fmin(gap, qz - (g.oz + bz0 * g.cell));
+    if (bz1 < g.cnz - 1) gap = fmin(gap, (g.oz + (bz1 + 1) * g.cell) - qz);
+    gap -= 1e-6 * g.cell;  // absorbs rounding in the particle -> cell assignment
+    const bool done = !active || (count >= k && gap > 0.0 && thr < gap * gap);
+    if (__syncthreads_and(done ? 1 : 0)) break;
+    have_prev = true;
+    pbx0 = bx0; pbx1 = bx1; pby0 = by0; pby1 = by1; pbz0 = bz0; pbz1 = bz1;
+    r += 1;
+  }
+
+  if (!valid) return;
+  if (!active) {
+    store_out<OutT>(p.u, vox, 0.0);
+    store_out<OutT>(p.v, vox, 0.0);
+    store_out<OutT>(p.w, vox, 0.0);
+    if (p.knn_idx) {
+      for (int j = 0; j < k; ++j) {
+        p.knn_idx[vox * k + j] = -1;
+        p.knn_dist[vox * k + j] = nan("");
+      }
+    }
+    return;
+  }
+
+  const int kk = count;  // == k whenever Np >= k (checked on the host)
+  if (kk < k) {
+    // heap property was never established; order for the outputs below is fixed by the sort
+    for (int h = kk / 2 - 1; h >= 0; --h) sift_down<T>(hk, hi, kk, h, hk[h * T], hi[h * T]);
+  }
+
+  if (p.knn_idx) {
+    // in-place heap sort -> ascending (d2, index); only taken by the parity tests
+    for (int n = kk; n > 1; --n) {
+      const double lk = hk[(n - 1) * T];
+      const int li = hi[(n - 1) * T];
+      hk[(n - 1) * T] = hk[0];
+      hi[(n - 1) * T] = hi[0];
+      sift_down<T>(hk, hi, n - 1, 0, lk, li);
+    }
+    for (int j = 0; j < k; ++j) {
+      p.knn_idx[vox * k + j] = j < kk ? (int64_t)hi[j * T] : (int64_t)g.n;
+      p.knn_dist[vox * k + j] = j < kk ? sqrt(hk[j * T]) : INFINITY;
+    }
+  }
+
+  double su = 0.0, sv = 0.0, sw = 0.0;
+  if (p.method == PTV_METHOD_NEAREST || (p.method == PTV_METHOD_IDW && kk == 1)) {
+    // k = 1: the weight cancels; copy the value (griddata 'nearest', interpolator.py:197)
+    int best = 0;
+    for (int j = 1; j < kk; ++j)
+      if (key_greater(hk[best * T], hi[best * T], hk[j * T], hi[j * T])) best = j;
+    const Value4 val = g.vals[hi[best * T]];
+    su = val.u; sv = val.v; sw = val.w;
+  } else if (p.method == PTV_METHOD_IDW) {
+    // interpolator.py:141-153: w = 1/(d**p + 1e-10), out = sum(w*val)/sum(w)
+    const double eps = 1e-10;
+    const bool p2 = (p.power == 2.0);
+    double wsum = 0.0;
+    for (int j = 0; j < kk; ++j) {
+      const double d2 = hk[j * T];
+      const double dp = p2 ? d2 : pow(sqrt(d2), p.power);
+      const double wgt = 1.0 / (dp + eps);
+      const Value4 val = g.vals[hi[j * T]];
+      wsum += wgt;
+      su += wgt * val.u;
+      sv += wgt * val.v;
+      sw += wgt * val.w;
+    }
+    su /= wsum; sv /= wsum; sw /= wsum;
+  } else {  // PTV_METHOD_SIBSON, interpolator.py:102-122
+    const double eps = 1e-10;
+    double dsum = 0.0, asum = 0.0;
+    for (int j = 0; j < kk; ++j) {
+      const double d = sqrt(hk[j * T]);
+      hk[j * T] = d;  // keep the distance for the next passes
+      dsum += d;
+      asum += 1.0 / (d + eps);
+    }
+    const double mean = dsum / kk;
+    double var = 0.0;
+    for (int j = 0; j < kk; ++j) {
+      const double e = hk[j * T] - mean;
+      var += e * e;
+    }
+    const double sd = sqrt(var / kk);  // population std, ddof = 0 (interpolator.py:113)
+    const double inv_s = 1.0 / (sd + eps);
+    double wsum = 0.0;
+    for (int j = 0; j < kk; ++j) {
+      const double d = hk[j * T];
+      const double wgt = ((1.0 / (d + eps)) / asum) * exp(-d * inv_s);
+      const Value4 val = g.vals[hi[j * T]];
+      wsum += wgt;
+      su += wgt * val.u;
+      sv += wgt * val.v;
+      sw += wgt * val.w;
+    }
+    su /= wsum; sv /= wsum; sw /= wsum;
+  }
+  // main.py:195-199 nan_to_num: NaN -> 0 (cannot arise from finite inputs; kept for parity)
+  if (su != su) su = 0.0;
+  if (sv != sv) sv = 0.0;
+  if (sw != sw) sw = 0.0;
+  store_out<OutT>(p.u, vox, su);
+  store_out<OutT>(p.v, vox, sv);
+  store_out<OutT>(p.w, vox, sw);
+}
+
+static size_t knn_smem_bytes(int T, int k) {
+  const int NW = T / 32;
+  size_t b = (size_t)k * T * sizeof(double) + (size_t)kStageCap * sizeof(ParticleRec) +
+             (size_t)6 * NW * sizeof(double) + (size_t)k * T * sizeof(int) +
+             (size_t)(2 * T + 1 + NW) * sizeof(int);
+  return (b + 15) & ~(size_t)15;
+}
+
+template <int T, int TX, int TY, int TZ, typename OutT>
+static int launch_knn(KnnParams& p, cudaStream_t stream) {
+  p.tiles_x = (p.nx + TX - 1) / TX;
+  p.tiles_y = (p.ny + TY - 1) / TY;
+  p.tiles_z = (p.nz + TZ - 1) / TZ;
+  const int64_t ntiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
+  if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
+  const size_t smem = knn_smem_bytes(T, p.k);
+  auto kern = knn_interp_kernel<T, TX, TY, TZ, OutT>;
+  PTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)ntiles, T, smem, stream>>>(p);
+  count_launches(1);
+  PTV_CUDA(cudaGetLastError());
+  return PTV_OK;
+}
+
+}  // namespace ptv
+
+using namespace ptv;
+
+extern "C" int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, const double* d_ax_y, int ny,
+                              const double* d_ax_z, int nz, const uint8_t* d_mask, int method, int k,
+                              double idw_power, double rbf_smoothing, int out_dtype, void* d_u, void* d_v,
+                              void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream_) {
+  (void)rbf_smoothing;
+  if (!h || !h->built) { set_error("ptv_knn_interp: hash not built"); return PTV_ERR_INVALID; }
+  if (!d_ax_x || !d_ax_y || !d_ax_z || !d_u || !d_v || !d_w) { set_error("ptv_knn_interp: NULL argument"); return PTV_ERR_INVALID; }
+  if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_knn_interp: empty grid"); return PTV_ERR_INVALID; }
+  if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_interp: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
+  if (method == PTV_METHOD_NEAREST) k = 1;
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST) {
+    set_error("ptv_knn_interp: unsupported method");
+    return PTV_ERR_INVALID;
+  }
+  if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_interp: bad out_dtype"); return PTV_ERR_INVALID; }
+  if (k < 1) { set_error("ptv_knn_interp: k must be >= 1"); return PTV_ERR_INVALID; }
+  if ((int64_t)k > h->n) {
+    // values[indices] with index == Np: IndexError in the reference (interpolator.py:150)
+    set_error("index " + std::to_string(h->n) + " is out of bounds for axis 0 with size " + std::to_string(h->n));
+    return PTV_ERR_TOO_FEW;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KnnParams p;
+  p.g = h->view();
+  p.ax = d_ax_x; p.ay = d_ax_y; p.az = d_ax_z;
+  p.nx = nx; p.ny = ny; p.nz = nz;
+  p.mask = d_mask; p.method = method; p.k = k; p.power = idw_power;
+  p.u = d_u; p.v = d_v; p.w = d_w;
+  p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
+  p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
+
+  const size_t smem_max = 227 * 1024;
+  int T = tuning().tile;
+  if (T != 32 && T != 64 && T != 128) T = 128;
+  while (T > 32 && knn_smem_bytes(T, k) > smem_max / 2) T >>= 1;  // keep >= 2 CTAs per SM if possible
+  if (knn_smem_bytes(T, k) > smem_max) {
+    set_error("ptv_knn_interp: k too large for shared memory (max ~580)");
+    return PTV_ERR_INVALID;
+  }
+  const bool f32 = out_dtype == PTV_F32;
+  switch (T) {
+    case 128: return f32 ? launch_knn<128, 8, 4, 4, float>(p, stream) : launch_knn<128, 8, 4, 4, double>(p, stream);
+    case 64: return f32 ? launch_knn<64, 4, 4, 4, float>(p, stream) : launch_knn<64, 4, 4, 4, double>(p, stream);
+    default: return f32 ? launch_knn<32, 4, 4, 2, float>(p, stream) : launch_knn<32, 4, 4, 2, double>(p, stream);
+  }
+}

@@ -1,0 +1,77 @@
+// Internal declarations shared by the .cu translation units of libptvb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "ptv_b200.h"
+
+namespace ptv {
+
+// One cell-sorted particle record: 32 B, 16-B aligned so a row of cells is one contiguous,
+// bulk-copyable range.  `idx` is the particle's ORIGINAL row (ties are broken on it).
+struct __align__(16) ParticleRec {
+  double x, y, z;
+  int32_t idx;
+  int32_t pad;
+};
+static_assert(sizeof(ParticleRec) == 32, "ParticleRec must be 32 bytes");
+
+struct __align__(16) Value4 {  // (u,v,w,0) in ORIGINAL particle order
+  double u, v, w, pad;
+};
+
+struct HashGrid {  // plain-old-data view passed to kernels by value
+  const ParticleRec* rec;
+  const int32_t* cell_start;  // [ncells+1], cell id = (cz*cny + cy)*cnx + cx
+  const Value4* vals;
+  const double* pts;          // original (n,3) float64 rows (caller-owned; valid during the call that set it)
+  double ox, oy, oz;          // origin = particle bbox minimum
+  double cell, inv_cell;
+  int cnx, cny, cnz;
+  int64_t n;
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+struct Tuning {
+  double ppc = 1.0;  // target particles per cell
+  int r0 = 1;        // rings merged into the first staging batch
+  int tile = 128;    // threads (= voxels) per tile
+};
+Tuning& tuning();
+void count_launches(int n);
+
+#define PTV_CUDA(expr)                                                    \
+  do {                                                                    \
+    cudaError_t _e = (expr);                                              \
+    if (_e != cudaSuccess) return ::ptv::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace ptv
+
+struct ptv_hash {
+  // device buffers (grown on demand, reused across builds)
+  ptv::ParticleRec* rec = nullptr;
+  ptv::Value4* vals = nullptr;
+  int32_t* cid = nullptr;
+  int32_t* sorted_idx = nullptr;
+  int32_t* cell_start = nullptr;  // ncells+1
+  int32_t* cell_fill = nullptr;   // ncells
+  int32_t* scan_tmp = nullptr;
+  double* bbox_dev = nullptr;     // 6 doubles + scratch partials
+  double* bbox_host = nullptr;    // pinned, 8 doubles
+  int64_t cap_n = 0;
+  int64_t cap_cells = 0;
+  int64_t cap_scan = 0;
+  // geometry of the last build
+  int64_t n = 0;
+  int dims[3] = {0, 0, 0};
+  double origin[3] = {0, 0, 0};
+  double cell = 0;
+  int max_cell_count = 0;
+  const double* pts = nullptr;
+  bool built = false;
+  ptv::HashGrid view() const;
+};

@@ -1,0 +1,84 @@
+"""z-slab sharding of the voxel grid across ranks (one process per GPU, torch.distributed).
+
+The interpolation itself needs no data-path collective: every rank holds the particle cloud and
+interpolates its own contiguous block of z-planes.  The exchange steps are the ones the path
+really has: one-plane halos of ``w`` and ``mask`` between z-neighbours for the
+z-term of the divergence stencil (physics.py:49-53), and sum-reductions of the flux profiles and
+of (sum|div|, n_fluid).  Works on NCCL (CUDA tensors) and gloo (CPU tensors, used by the tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["slab_range", "SlabComm"]
+
+
+def slab_range(nz: int, world: int, rank: int):
+    """Contiguous z-planes [z0, z1) of ``rank``: the first ``nz % world`` ranks get one extra."""
+    base, rem = divmod(nz, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, z0 + base + (1 if rank < rem else 0)
+
+
+class SlabComm:
+    """Halo exchange + reductions for one slab decomposition.  With world == 1 every method is a
+    no-op that returns the local data."""
+
+    def __init__(self, nz: int, group=None):
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.nz = nz
+        self.z0, self.z1 = slab_range(nz, self.world, self.rank)
+        # neighbours that own at least one plane
+        self.lower = self.rank - 1 if self.rank > 0 else None
+        self.upper = self.rank + 1 if self.rank + 1 < self.world else None
+
+    def exchange_halos(self, w_slab: torch.Tensor, mask_slab: torch.Tensor):
+        """Returns (w_below, w_above, mask_above): the (ny,nx) planes z0-1 and z1 owned by the
+        z-neighbours (None at the domain edges -> Neumann edge rule of physics.py:38-45)."""
+        if self.world == 1:
+            return None, None, None
+        if self.z1 - self.z0 < 1:
+            raise ValueError("every rank must own at least one z-plane")
+        ops, w_below, w_above, m_above = [], None, None, None
+        first_w = w_slab[0].contiguous()
+        last_w = w_slab[-1].contiguous()
+        first_m = mask_slab[0].contiguous()
+        if self.lower is not None:  # my first plane is the lower neighbour's "above"
+            w_below = torch.empty_like(first_w)
+            ops += [dist.P2POp(dist.isend, first_w, self.lower, self.group),
+                    dist.P2POp(dist.isend, first_m, self.lower, self.group),
+                    dist.P2POp(dist.irecv, w_below, self.lower, self.group)]
+        if self.upper is not None:
+            w_above = torch.empty_like(last_w)
+            m_above = torch.empty_like(first_m)
+            ops += [dist.P2POp(dist.isend, last_w, self.upper, self.group),
+                    dist.P2POp(dist.irecv, w_above, self.upper, self.group),
+                    dist.P2POp(dist.irecv, m_above, self.upper, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        return w_below, w_above, m_above
+
+    def reduce_sum_(self, *tensors):
+        """In-place SUM all-reduce of small float64 tensors (flux profiles, statistics)."""
+        if self.world > 1:
+            flat = torch.cat([t.reshape(-1) for t in tensors])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            o = 0
+            for t in tensors:
+                n = t.numel()
+                t.copy_(flat[o:o + n].view_as(t))
+                o += n
+        return tensors
+
+    def gather_planes(self, q_local: torch.Tensor):
+        """Concatenate a per-plane profile (e.g. Q_xy[z] of the local slab) over ranks."""
+        if self.world == 1:
+            return q_local
+        full = torch.zeros(self.nz, dtype=q_local.dtype, device=q_local.device)
+        full[self.z0:self.z1] = q_local
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+        return full

@@ -1,0 +1,212 @@
+"""Device-resident engine: torch owns device memory and streams, libptvb200.so does the work.
+
+The engine keeps one spatial hash (buffers reused across rebuilds, e.g. per PTV frame) and
+exposes the hot path on device tensors; ``interpolator.py`` / ``physics.py`` wrap it with the
+reference's NumPy signatures.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_METHODS = {"idw": _cabi.METHOD_IDW, "sibson": _cabi.METHOD_SIBSON, "nearest": _cabi.METHOD_NEAREST,
+            "rbf": _cabi.METHOD_RBF}
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _cabi.PTVError("ptv_interpolation_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise _cabi.PTVError(f"device must be a CUDA device, got {dev}")
+    return dev
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return _cabi.F32
+    if dt == torch.float64:
+        return _cabi.F64
+    raise ValueError(f"unsupported field dtype {dt}")
+
+
+class PTVEngine:
+    """One spatial hash + the kernels that consume it, bound to one CUDA device."""
+
+    def __init__(self, device=None):
+        self.lib = _cabi.load()
+        self.device = _require_cuda(device)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_hash_create(C.byref(self._h)))
+        self._keep = None  # tensors the hash borrows
+
+    def close(self):
+        if self._h:
+            self.lib.ptv_hash_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ hash
+    def build(self, points: torch.Tensor, values: torch.Tensor, cell_size: float = 0.0):
+        """points, values: (Np,3) float64 CUDA tensors (df[['x','y','z']], df[['u','v','w']])."""
+        if points.dtype != torch.float64 or values.dtype != torch.float64:
+            raise ValueError("points and values must be float64")
+        if points.ndim != 2 or points.shape[1] != 3 or values.shape != points.shape:
+            raise ValueError("points and values must both have shape (Np, 3)")
+        points = points.contiguous()
+        values = values.contiguous()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_hash_build(self._h, _ptr(points), _ptr(values), points.shape[0],
+                                                float(cell_size), self._stream()))
+        self._keep = (points, values)
+        self.n_particles = points.shape[0]
+
+    def hash_info(self):
+        n = C.c_int64()
+        dims = (C.c_int * 3)()
+        origin = (C.c_double * 3)()
+        cell = C.c_double()
+        mx = C.c_int()
+        _cabi.check(self.lib.ptv_hash_info(self._h, C.byref(n), C.byref(dims), C.byref(origin), C.byref(cell),
+                                           C.byref(mx)))
+        return {"n": n.value, "dims": tuple(dims), "origin": tuple(origin), "cell": cell.value,
+                "max_cell_count": mx.value}
+
+    # ------------------------------------------------------------------ interpolation
+    def interpolate(self, ax_x, ax_y, ax_z, mask=None, method="idw", k=50, idw_power=2.0, smoothing=0.0,
+                    out_dtype=torch.float32, out=None, return_knn=False):
+        """Fused kNN + weights on the rectilinear grid ax_x (x) ax_y (x) ax_z (float64 CUDA axes).
+        mask: optional (nz,ny,nx) uint8/bool CUDA tensor, non-zero = pore.  Returns a (3,nz,ny,nx)
+        tensor (U,V,W) and, if ``return_knn``, (dist (nvox,k) float64, idx (nvox,k) int64)."""
+        if method not in _METHODS:
+            raise NotImplementedError(f"method {method!r} is not on the CUDA path")
+        nx, ny, nz = ax_x.numel(), ax_y.numel(), ax_z.numel()
+        for a in (ax_x, ax_y, ax_z):
+            if a.dtype != torch.float64 or not a.is_cuda:
+                raise ValueError("grid axes must be float64 CUDA tensors")
+        ax_x, ax_y, ax_z = ax_x.contiguous(), ax_y.contiguous(), ax_z.contiguous()
+        if mask is not None:
+            if mask.dtype == torch.bool:
+                mask = mask.view(torch.uint8)
+            if mask.dtype != torch.uint8 or tuple(mask.shape) != (nz, ny, nx):
+                raise ValueError("mask must be uint8/bool with shape (nz, ny, nx)")
+            mask = mask.contiguous()
+        if out is None:
+            out = torch.empty((3, nz, ny, nx), dtype=out_dtype, device=self.device)
+        elif tuple(out.shape) != (3, nz, ny, nx) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous (3, nz, ny, nx) tensor")
+        if method == "nearest":
+            k = 1
+        kd = ki = None
+        if return_knn:
+            ki = torch.empty((nz * ny * nx, k), dtype=torch.int64, device=self.device)
+            kd = torch.empty((nz * ny * nx, k), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_knn_interp(self._h, _ptr(ax_x), nx, _ptr(ax_y), ny, _ptr(ax_z), nz, _ptr(mask),
+                                                _METHODS[method], int(k), float(idw_power), float(smoothing),
+                                                _dtype_code(out.dtype), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                                _ptr(ki), _ptr(kd), self._stream()))
+        if return_knn:
+            return out, kd, ki
+        return out
+
+    # ------------------------------------------------------------------ grid ops
+    def mask_gather(self, mask_raw, ix, iy, iz):
+        rnz, rny, rnx = mask_raw.shape
+        if mask_raw.dtype == torch.bool:
+            mask_raw = mask_raw.view(torch.uint8)
+        mask_raw = mask_raw.contiguous()
+        out = torch.empty((iz.numel(), iy.numel(), ix.numel()), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_mask_gather(_ptr(mask_raw), rnx, rny, rnz, _ptr(ix), ix.numel(), _ptr(iy),
+                                                 iy.numel(), _ptr(iz), iz.numel(), _ptr(out), self._stream()))
+        return out
+
+    def boundary_voxels(self, mask, thickness=1):
+        """Linear C-order indices (int64 CUDA tensor) of solid voxels within ``thickness``
+        6-connected dilation steps of fluid."""
+        nz, ny, nx = mask.shape
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        mask = mask.contiguous()
+        cnt = C.c_int64()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_boundary_voxels(_ptr(mask), nx, ny, nz, int(thickness), None, 0,
+                                                     C.byref(cnt), self._stream()))
+            idx = torch.empty((cnt.value,), dtype=torch.int64, device=self.device)
+            if cnt.value:
+                _cabi.check(self.lib.ptv_boundary_voxels(_ptr(mask), nx, ny, nz, int(thickness), _ptr(idx),
+                                                         cnt.value, C.byref(cnt), self._stream()))
+        return idx
+
+    def apply_mask(self, uvw, mask):
+        if mask is not None and mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        n = uvw[0].numel()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_apply_mask(_ptr(uvw[0]), _ptr(uvw[1]), _ptr(uvw[2]), _ptr(mask), n,
+                                                _dtype_code(uvw.dtype), self._stream()))
+        return uvw
+
+    def divergence(self, u, v, w, mask, dx, dy, dz, w_below=None, w_above=None, mask_above=None,
+                   with_stats=False):
+        nz, ny, nx = u.shape
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        if mask_above is not None and mask_above.dtype == torch.bool:
+            mask_above = mask_above.view(torch.uint8)
+        u, v, w, mask = u.contiguous(), v.contiguous(), w.contiguous(), mask.contiguous()
+        div = torch.empty_like(u)
+        stats = torch.zeros(2, dtype=torch.float64, device=self.device) if with_stats else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_divergence(_ptr(u), _ptr(v), _ptr(w), _ptr(mask), nx, ny, nz, float(dx),
+                                                float(dy), float(dz), _ptr(w_below), _ptr(w_above),
+                                                _ptr(mask_above), _dtype_code(u.dtype), _ptr(div), _ptr(stats),
+                                                self._stream()))
+        return (div, stats) if with_stats else div
+
+    def flux_profiles(self, u, v, w):
+        """Unscaled plane sums (q_xy[nz], q_xz[ny], q_yz[nx]) as float64 CUDA tensors."""
+        ref = next(t for t in (u, v, w) if t is not None)
+        nz, ny, nx = ref.shape
+        qxy = torch.zeros(nz, dtype=torch.float64, device=self.device)
+        qxz = torch.zeros(ny, dtype=torch.float64, device=self.device)
+        qyz = torch.zeros(nx, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_flux_profiles(_ptr(u), _ptr(v), _ptr(w), nx, ny, nz, _dtype_code(ref.dtype),
+                                                   _ptr(qxy), _ptr(qxz), _ptr(qyz), self._stream()))
+        return qxy, qxz, qyz
+
+
+_default_engine = {}
+
+
+def default_engine(device=None) -> PTVEngine:
+    dev = _require_cuda(device)
+    key = (dev.type, dev.index)
+    if key not in _default_engine:
+        _default_engine[key] = PTVEngine(dev)
+    return _default_engine[key]
+
+
+def set_tuning(**kw):
+    lib = _cabi.load()
+    for k, v in kw.items():
+        _cabi.check(lib.ptv_set_tuning(k.encode(), float(v)))

@@ -1,0 +1,199 @@
+"""Drop-in mirror of the reference's ``interpolator.py`` public API, backed by the sm_100a
+CUDA path (libptvb200.so).  Same names, argument meaning and error behaviour:
+
+    load_ptv_data, load_mask, create_grid, interpolate_field, sample_mask_on_grid,
+    extract_boundary_particles                       (reference interpolator.py:9,28,41,65,205,240)
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * ``create_grid`` returns read-only zero-stride broadcast views for X, Y, Z (same values and
+    shapes; 24 B/voxel of coordinates are never materialised);
+  * ``interpolate_field`` returns float32 arrays by default (``out_dtype=np.float64`` restores the
+    reference dtype), accepts an optional ``mask=`` to skip and zero solid voxels (what
+    main.py:202-207 does afterwards), and writes 0 where the reference would produce NaN
+    (main.py:195-199 replaces those by 0 anyway);
+  * ``method='linear'/'cubic'`` (Delaunay via griddata, interpolator.py:197) are not on the CUDA
+    path and raise NotImplementedError -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import default_engine
+
+__all__ = ["load_ptv_data", "load_mask", "create_grid", "interpolate_field", "sample_mask_on_grid",
+           "extract_boundary_particles"]
+
+_GPU_METHODS = ("idw", "sibson", "nearest", "rbf")
+
+
+def load_ptv_data(filepath):
+    """interpolator.py:9-26 -- CSV with x,y,z,u,v,w (or vx,vy,vz); any failure -> IOError."""
+    try:
+        import pandas as pd
+        df = pd.read_csv(filepath)
+        df.rename(columns={"vx": "u", "vy": "v", "vz": "w"}, inplace=True)
+        required_cols = {"x", "y", "z", "u", "v", "w"}
+        if not required_cols.issubset(df.columns):
+            raise ValueError(f"CSV must contain columns: {required_cols}")
+        return df
+    except Exception as e:
+        raise IOError(f"Error reading {filepath}: {e}")
+
+
+def load_mask(filepath):
+    """interpolator.py:28-39 -- 3-D TIFF (or .npy when tifffile is unavailable) -> bool, True = fluid."""
+    try:
+        if str(filepath).endswith(".npy"):
+            mask = np.load(filepath)
+        else:
+            import tifffile
+            mask = tifffile.imread(filepath)
+        return mask > 0
+    except Exception as e:
+        raise IOError(f"Error reading mask {filepath}: {e}")
+
+
+def create_grid(bounds, resolution):
+    """interpolator.py:41-60 -- axes ``linspace(min, max-1, n)``; X, Y, Z of shape (nz, ny, nx)."""
+    (xmin, xmax), (ymin, ymax), (zmin, zmax) = bounds
+    if isinstance(resolution, int):
+        nx = ny = nz = resolution
+    else:
+        nx, ny, nz = resolution
+    x = np.linspace(xmin, xmax - 1, nx)
+    y = np.linspace(ymin, ymax - 1, ny)
+    z = np.linspace(zmin, zmax - 1, nz)
+    shape = (nz, ny, nx)
+    X = np.broadcast_to(x[None, None, :], shape)
+    Y = np.broadcast_to(y[None, :, None], shape)
+    Z = np.broadcast_to(z[:, None, None], shape)
+    return (X, Y, Z), (x, y, z)
+
+
+def _grid_axes(grid_tuple):
+    """Recover the three float64 axes of a rectilinear (nz,ny,nx) meshgrid; zero-stride views are
+    recognised without touching memory, dense meshgrids are verified."""
+    X, Y, Z = (np.asarray(a) for a in grid_tuple)
+    if X.ndim != 3 or X.shape != Y.shape or X.shape != Z.shape:
+        raise ValueError("grid_tuple must hold three (nz, ny, nx) arrays")
+    x = np.ascontiguousarray(X[0, 0, :], dtype=np.float64)
+    y = np.ascontiguousarray(Y[0, :, 0], dtype=np.float64)
+    z = np.ascontiguousarray(Z[:, 0, 0], dtype=np.float64)
+
+    def is_bcast(a, axis):
+        return all(a.strides[i] == 0 or a.shape[i] == 1 for i in range(3) if i != axis)
+
+    if not (is_bcast(X, 2) and is_bcast(Y, 1) and is_bcast(Z, 0)):
+        ok = (np.array_equal(X, np.broadcast_to(X[0:1, 0:1, :], X.shape))
+              and np.array_equal(Y, np.broadcast_to(Y[0:1, :, 0:1], Y.shape))
+              and np.array_equal(Z, np.broadcast_to(Z[:, 0:1, 0:1], Z.shape)))
+        if not ok:
+            raise NotImplementedError("interpolate_field: only rectilinear (meshgrid) query grids are "
+                                      "on the CUDA path")
+    return x, y, z
+
+
+def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_kernel="thin_plate_spline",
+                      smoothing=0.0, n_jobs=1, idw_power=2.0, idw_neighbors=50, sibson_neighbors=30,
+                      mask=None, out_dtype=np.float32, device=None, return_knn=False):
+    """interpolator.py:65-203.  ``n_jobs`` is accepted and ignored (one GPU does the work).
+    Returns (U, V, W): three writable (nz, ny, nx) views of one host array, like the reference."""
+    import torch
+    points = df[["x", "y", "z"]].values
+    values = df[["u", "v", "w"]].values
+    if method not in _GPU_METHODS:
+        raise NotImplementedError(
+            f"method={method!r} (scipy griddata / Delaunay, interpolator.py:197) is not implemented on the "
+            f"CUDA path; supported methods: {_GPU_METHODS}")
+    if method == "rbf" and rbf_kernel != "thin_plate_spline":
+        raise NotImplementedError("only rbf_kernel='thin_plate_spline' is on the CUDA path")
+    x, y, z = _grid_axes(grid_tuple)
+    eng = default_engine(device)
+    dev = eng.device
+    pts = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev)
+    vals = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
+    k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors}[method]
+    if method == "rbf":
+        k = min(int(k), len(points))  # scipy _rbfinterp.py:313 clamps silently
+    eng.build(pts, vals)
+    ax = [torch.from_numpy(a).to(dev) for a in (x, y, z)]
+    m = None
+    if mask is not None:
+        m = torch.from_numpy(np.ascontiguousarray(mask).astype(np.uint8, copy=False)).to(dev)
+    tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
+    res = eng.interpolate(ax[0], ax[1], ax[2], mask=m, method=method, k=int(k), idw_power=float(idw_power),
+                          smoothing=float(smoothing), out_dtype=tdt, return_knn=return_knn)
+    if return_knn:
+        out, kd, ki = res
+    else:
+        out = res
+    host = out.cpu().numpy()
+    U, V, W = host[0], host[1], host[2]
+    if return_knn:
+        return U, V, W, kd.cpu().numpy(), ki.cpu().numpy()
+    return U, V, W
+
+
+def _nearest_axis_index(src_coords, q):
+    """RegularGridInterpolator(method='nearest', bounds_error=False) along one axis
+    (scipy _rgi.py:551-554, 632-642): interval i, offset (q-g[i])/(g[i+1]-g[i]), <= 0.5 -> i else
+    i+1; -1 where q lies outside [g[0], g[-1]]."""
+    g = np.asarray(src_coords, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    n = len(g)
+    if n == 1:
+        idx = np.zeros(q.shape, dtype=np.int64)
+    else:
+        i = np.clip(np.searchsorted(g, q, side="right") - 1, 0, n - 2)
+        yi = (q - g[i]) / (g[i + 1] - g[i])
+        idx = np.where(yi <= 0.5, i, i + 1).astype(np.int64)
+    idx[(q < g[0]) | (q > g[-1])] = -1
+    return idx.astype(np.int32)
+
+
+def sample_mask_on_grid(mask_raw, grid_tuple, bounds_raw, device=None):
+    """interpolator.py:205-238 -- nearest-neighbour resampling of ``mask_raw`` onto the grid."""
+    import torch
+    mask_raw = np.asarray(mask_raw)
+    nz, ny, nx = mask_raw.shape
+    (xmin, xmax), (ymin, ymax), (zmin, zmax) = bounds_raw
+    x, y, z = _grid_axes(grid_tuple)
+    z_coords = np.linspace(zmin, zmax - 1, nz) if nz > 1 else np.array([zmin])
+    y_coords = np.linspace(ymin, ymax - 1, ny) if ny > 1 else np.array([ymin])
+    x_coords = np.linspace(xmin, xmax - 1, nx) if nx > 1 else np.array([xmin])
+    eng = default_engine(device)
+    dev = eng.device
+    ix = torch.from_numpy(_nearest_axis_index(x_coords, x)).to(dev)
+    iy = torch.from_numpy(_nearest_axis_index(y_coords, y)).to(dev)
+    iz = torch.from_numpy(_nearest_axis_index(z_coords, z)).to(dev)
+    # mask_raw.astype(float) > 0.5 after nearest lookup == (value != 0) for bool / 0-1 masks;
+    # general numeric masks are thresholded the same way the reference does (:238)
+    raw = (mask_raw.astype(float) > 0.5) if mask_raw.dtype != np.bool_ else mask_raw
+    raw_t = torch.from_numpy(np.ascontiguousarray(raw).view(np.uint8)).to(dev)
+    out = eng.mask_gather(raw_t, ix, iy, iz)
+    return out.cpu().numpy().astype(bool)
+
+
+def extract_boundary_particles(mask, bounds, sampling_step=1, thickness=1, device=None):
+    """interpolator.py:240-284 -- coordinates of solid voxels within ``thickness`` dilation steps
+    of the fluid, every ``sampling_step``-th in C order, for zero-velocity wall particles."""
+    import torch
+    if mask is None:
+        return np.array([]), np.array([]), np.array([])
+    mask = np.asarray(mask)
+    nz, ny, nx = mask.shape
+    (xmin, xmax), (ymin, ymax), (zmin, zmax) = bounds
+    eng = default_engine(device)
+    m = torch.from_numpy(np.ascontiguousarray(mask != 0).view(np.uint8)).to(eng.device)
+    lin = eng.boundary_voxels(m, thickness=int(thickness))
+    if lin.numel() == 0:
+        return np.array([]), np.array([]), np.array([])
+    if sampling_step > 1:
+        lin = lin[::sampling_step]
+    lin = lin.cpu().numpy()
+    Z_idx, rem = np.divmod(lin, ny * nx)
+    Y_idx, X_idx = np.divmod(rem, nx)
+    z_phys = zmin + Z_idx * (zmax - 1 - zmin) / (nz - 1) if nz > 1 else np.full_like(Z_idx, zmin)
+    y_phys = ymin + Y_idx * (ymax - 1 - ymin) / (ny - 1) if ny > 1 else np.full_like(Y_idx, ymin)
+    x_phys = xmin + X_idx * (xmax - 1 - xmin) / (nx - 1) if nx > 1 else np.full_like(X_idx, xmin)
+    return x_phys, y_phys, z_phys

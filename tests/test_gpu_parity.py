@@ -1,0 +1,269 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the
+golden vectors of the live reference.  Bars: neighbour indices, distances and mask bits exact;
+velocities |gpu-ref| <= 1e-5 * max(|ref|, rms(input component))."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from oracle import reference_port as rp  # noqa: E402
+from ptv_interpolation_b200 import interpolator as gi  # noqa: E402
+from ptv_interpolation_b200 import physics as gp  # noqa: E402
+from ptv_interpolation_b200 import synthetic  # noqa: E402
+from ptv_interpolation_b200.engine import PTVEngine, set_tuning  # noqa: E402
+
+TOL = 1e-5
+
+
+def _df(points, values):
+    return pd.DataFrame({"x": points[:, 0], "y": points[:, 1], "z": points[:, 2],
+                         "u": values[:, 0], "v": values[:, 1], "w": values[:, 2]})
+
+
+def _bounds(b):
+    return tuple(tuple(float(v) for v in row) for row in b)
+
+
+def _assert_vel(got, ref, values, tol=TOL):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    for c in range(3):
+        s = np.sqrt(np.mean(values[:, c] ** 2))
+        bound = tol * np.maximum(np.abs(ref[c]), s)
+        err = np.abs(got[c] - ref[c])
+        assert np.all(err <= bound), (c, float(err.max()), float((err / bound).max()))
+
+
+@pytest.fixture(scope="module")
+def case_a(golden_dir):
+    g = np.load(os.path.join(golden_dir, "case_a_interp.npz"))
+    grid, axes = gi.create_grid(_bounds(g["bounds"]), tuple(int(r) for r in g["res"]))
+    return g, grid, _df(g["points"], g["values"])
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("idw_k50", dict(method="idw")),
+    ("idw_k8_p3", dict(method="idw", idw_neighbors=8, idw_power=3.0)),
+    ("idw_k8_p15", dict(method="idw", idw_neighbors=8, idw_power=1.5)),
+    ("sibson_k30", dict(method="sibson")),
+    ("sibson_k12", dict(method="sibson", sibson_neighbors=12)),
+    ("nearest", dict(method="nearest")),
+])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_golden_interp(case_a, name, kw, dtype):
+    g, grid, df = case_a
+    U, V, W = gi.interpolate_field(df, grid, out_dtype=dtype, **kw)
+    assert U.dtype == dtype and U.shape == grid[0].shape and U.flags.writeable
+    _assert_vel(np.stack([U, V, W]), g[name], g["values"])
+    if dtype == np.float64:  # fp64 accumulate: far inside the fp32 bar
+        _assert_vel(np.stack([U, V, W]), g[name], g["values"], tol=1e-11)
+
+
+@pytest.mark.parametrize("k", [1, 8, 50])
+def test_golden_knn_bitexact(case_a, k):
+    g, grid, df = case_a
+    method = "nearest" if k == 1 else "idw"
+    U, V, W, kd, ki = gi.interpolate_field(df, grid, method=method, idw_neighbors=k, return_knn=True)
+    assert np.array_equal(ki, g[f"knn_i_k{k}"])
+    assert np.array_equal(kd, g[f"knn_d_k{k}"])
+
+
+def test_lattice_ties_canonical(golden_dir):
+    g = np.load(os.path.join(golden_dir, "case_b_boundary.npz"))
+    b = _bounds(g["bounds"])
+    grid, _ = gi.create_grid(b, 12)
+    pts, vals = g["points"], g["values"]
+    U, V, W, kd, ki = gi.interpolate_field(_df(pts, vals), grid, method="idw", idw_neighbors=20,
+                                           return_knn=True, out_dtype=np.float64)
+    _assert_vel(np.stack([U, V, W]), g["idw_k20"], vals)
+    og, _ = rp.create_grid(b, 12)
+    d, i, _ = rp.knn_canonical(pts, rp.flat_coords(og), 20)
+    assert np.array_equal(ki, i)
+    assert np.array_equal(kd, d)
+    # the same through the brute-force definition
+    d2, i2, _ = rp.knn_bruteforce(pts, rp.flat_coords(og), 20)
+    assert np.array_equal(ki, i2) and np.array_equal(kd, d2)
+
+
+def test_boundary_particles_and_mask_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "case_b_boundary.npz"))
+    b = _bounds(g["bounds"])
+    for th, st in ((1, 1), (2, 1), (2, 3), (3, 5)):
+        bx, by, bz = gi.extract_boundary_particles(g["mask_raw"], b, sampling_step=st, thickness=th)
+        assert np.array_equal(np.stack([bx, by, bz], 0).astype(np.float64), g[f"bp_t{th}_s{st}"])
+    grid, _ = gi.create_grid(b, 12)
+    assert np.array_equal(gi.sample_mask_on_grid(g["mask_raw"], grid, b), g["mask_grid"])
+    none = gi.extract_boundary_particles(np.ones((4, 5, 6), bool), ((0, 6), (0, 5), (0, 4)))
+    assert all(len(a) == 0 for a in none)
+
+
+@pytest.mark.parametrize("name", ["same", "down2", "down3", "shift", "up"])
+def test_mask_sampling_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "case_c_mask.npz"))
+    grid, _ = gi.create_grid(_bounds(g[f"{name}_bgrid"]), tuple(int(r) for r in g[f"{name}_res"]))
+    out = gi.sample_mask_on_grid(g["mask_raw"], grid, _bounds(g[f"{name}_braw"]))
+    assert out.dtype == bool and np.array_equal(out, g[f"{name}_out"])
+
+
+def test_divergence_flux_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "case_d_divergence.npz"))
+    dx, dy, dz = (float(h) for h in g["h"])
+    div = gp.compute_consistent_divergence(g["u"], g["v"], g["w"], g["mask"], dx, dy, dz)
+    assert div.dtype == np.float64 and np.array_equal(div, g["div"])
+    assert np.allclose(gp.calculate_flux_xy(g["w"], dx, dy), g["q_xy"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(gp.calculate_flux_xz(g["v"], dx, dz), g["q_xz"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(gp.calculate_flux_yz(g["u"], dy, dz), g["q_yz"], rtol=1e-12, atol=1e-12)
+    assert abs(gp.mid_plane_x_flux(g["u"], dy, dz) - float(g["mid_x"])) <= 1e-12 * max(1, abs(float(g["mid_x"])))
+    m = gp.mean_abs_divergence(g["u"], g["v"], g["w"], g["mask"], dx, dy, dz)
+    assert abs(m - float(g["mean_abs_div"])) <= 1e-12 * float(g["mean_abs_div"])
+    # float32 fields: stencil evaluated in float64 on the upcast field, result rounded to float32
+    u32, v32, w32 = (g[c].astype(np.float32) for c in "uvw")
+    d32 = gp.compute_consistent_divergence(u32, v32, w32, g["mask"], dx, dy, dz)
+    ref = rp.compute_consistent_divergence(u32.astype(np.float64), v32.astype(np.float64),
+                                           w32.astype(np.float64), g["mask"], dx, dy, dz)
+    assert d32.dtype == np.float32 and np.array_equal(d32, ref.astype(np.float32))
+
+
+def test_divergence_slab_halos_match_whole():
+    rng = np.random.default_rng(9)
+    shape = (12, 10, 9)
+    u, v, w = (rng.normal(size=shape) for _ in range(3))
+    m = rng.random(shape) > 0.3
+    ref = rp.compute_consistent_divergence(u, v, w, m, 1.0, 2.0, 0.5)
+    eng = PTVEngine()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pieces, tot = [], torch.zeros(2, dtype=torch.float64, device="cuda")
+    cuts = [0, 5, 6, 12]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        below = t(w[a - 1]) if a > 0 else None
+        above = t(w[b]) if b < shape[0] else None
+        mabove = t(m[b]).view(torch.uint8) if b < shape[0] else None
+        d, st = eng.divergence(t(u[a:b]), t(v[a:b]), t(w[a:b]), t(m[a:b]), 1.0, 2.0, 0.5, w_below=below,
+                               w_above=above, mask_above=mabove, with_stats=True)
+        pieces.append(d.cpu().numpy())
+        tot += st
+    assert np.array_equal(np.concatenate(pieces, 0), ref)
+    s, c = tot.cpu().numpy()
+    assert c == m.sum() and abs(s / c - rp.mean_abs_div(ref, m)) < 1e-13
+
+
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("method,k", [("idw", 50), ("sibson", 30), ("idw", 3)])
+def test_sphere_pack_vs_oracle(masked, method, k):
+    n = 40
+    mask = synthetic.hex6_sphere_pack_mask(n)
+    pts = synthetic.sample_pore_particles(mask, 6000, seed=11)
+    vals = synthetic.sphere_pack_flow(pts, n)
+    pts, vals, mask = pts.numpy(), vals.numpy(), mask.numpy()
+    b = ((0, n), (0, n), (0, n))
+    grid, _ = gi.create_grid(b, n)
+    kw = dict(method=method, idw_neighbors=k, sibson_neighbors=k)
+    U, V, W, kd, ki = gi.interpolate_field(_df(pts, vals), grid, mask=mask if masked else None,
+                                           return_knn=True, **kw)
+    og, _ = rp.create_grid(b, n)
+    Ur, Vr, Wr, d, i = rp.interpolate_field(pts, vals, og, return_knn=True, **kw)
+    ref = np.stack([Ur, Vr, Wr])
+    if masked:
+        ref = np.stack(rp.apply_mask_zero(Ur, Vr, Wr, mask))
+        sel = mask.ravel()
+        assert np.array_equal(ki[sel], i[sel]) and np.array_equal(kd[sel], d[sel])
+        assert np.all(ki[~sel] == -1)
+        assert np.all(np.stack([U, V, W])[:, ~mask] == 0)
+    else:
+        assert np.array_equal(ki, i) and np.array_equal(kd, d)
+    _assert_vel(np.stack([U, V, W]), ref, vals)
+
+
+@pytest.mark.parametrize("tune", [dict(tile=64), dict(tile=32), dict(r0=0), dict(r0=3), dict(ppc=0.3),
+                                  dict(ppc=6.0)])
+def test_tuning_does_not_change_neighbours(case_a, tune):
+    g, grid, df = case_a
+    try:
+        set_tuning(**tune)
+        U, V, W, kd, ki = gi.interpolate_field(df, grid, method="idw", idw_neighbors=50, return_knn=True)
+    finally:
+        set_tuning(tile=128, r0=1, ppc=1.0)
+    assert np.array_equal(ki, g["knn_i_k50"]) and np.array_equal(kd, g["knn_d_k50"])
+
+
+@pytest.mark.parametrize("k", [64, 130, 300])
+def test_large_k(k):
+    rng = np.random.default_rng(k)
+    pts = rng.uniform(0, 10, size=(700, 3)).astype(np.float32).astype(np.float64)
+    vals = rng.normal(size=(700, 3))
+    b = ((0, 10), (0, 10), (0, 10))
+    grid, _ = gi.create_grid(b, (7, 6, 5))
+    U, V, W, kd, ki = gi.interpolate_field(_df(pts, vals), grid, method="idw", idw_neighbors=k, return_knn=True)
+    og, _ = rp.create_grid(b, (7, 6, 5))
+    Ur, Vr, Wr, d, i = rp.interpolate_field(pts, vals, og, method="idw", idw_neighbors=k, return_knn=True)
+    assert np.array_equal(ki, i) and np.array_equal(kd, d)
+    _assert_vel(np.stack([U, V, W]), np.stack([Ur, Vr, Wr]), vals)
+
+
+def test_duplicates_clusters_and_far_queries():
+    rng = np.random.default_rng(77)
+    base = rng.uniform(0, 4, size=(150, 3)).astype(np.float32).astype(np.float64)
+    pts = np.concatenate([base, base[:60], base[:20], np.full((90, 3), 2.0)], 0)  # exact duplicates + a pile
+    vals = rng.normal(size=(len(pts), 3))
+    b = ((-20, 31), (-3, 9), (1, 5))  # grid reaching far outside the particle bounding box
+    res = (17, 6, 4)
+    grid, _ = gi.create_grid(b, res)
+    U, V, W, kd, ki = gi.interpolate_field(_df(pts, vals), grid, method="idw", idw_neighbors=25, return_knn=True,
+                                           out_dtype=np.float64)
+    og, _ = rp.create_grid(b, res)
+    d, i, _ = rp.knn_bruteforce(pts, rp.flat_coords(og), 25)
+    assert np.array_equal(ki, i) and np.array_equal(kd, d)
+    ref = rp.idw_from_knn(d, i, vals).reshape(og[0].shape + (3,))
+    _assert_vel(np.stack([U, V, W]), np.moveaxis(ref, -1, 0), vals)
+
+
+def test_known_answers_and_errors():
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(0, 9, size=(200, 3)).astype(np.float32).astype(np.float64)
+    pts[0] = (4.0, 4.0, 4.0)
+    grid, _ = gi.create_grid(((0, 10), (0, 10), (0, 10)), 10)
+    U, V, W = gi.interpolate_field(_df(pts, np.full((200, 3), 7.0)), grid, method="idw", idw_neighbors=10)
+    assert np.allclose(U, 7.0, rtol=1e-6)
+    vals = rng.normal(size=(200, 3))
+    U, V, W = gi.interpolate_field(_df(pts, vals), grid, method="idw", idw_neighbors=10, out_dtype=np.float64)
+    assert abs(U[4, 4, 4] - vals[0, 0]) <= 1e-7 * max(1.0, abs(vals[0, 0]))
+    with pytest.raises(IndexError):
+        gi.interpolate_field(_df(pts[:5], vals[:5]), grid, method="idw", idw_neighbors=10)
+    bad = pts.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises(ValueError):
+        gi.interpolate_field(_df(bad, vals), grid, method="idw", idw_neighbors=10)
+    with pytest.raises(NotImplementedError):
+        gi.interpolate_field(_df(pts, vals), grid, method="linear")
+    # dense (np.meshgrid) grids as the reference builds them are accepted too
+    og, _ = rp.create_grid(((0, 10), (0, 10), (0, 10)), 10)
+    U2, _, _ = gi.interpolate_field(_df(pts, vals), og, method="idw", idw_neighbors=10, out_dtype=np.float64)
+    assert np.array_equal(U, U2)
+
+
+def test_host_cabi_entry_point():
+    import ctypes as C
+    from ptv_interpolation_b200 import _cabi
+    lib = _cabi.load()
+    rng = np.random.default_rng(3)
+    pts = np.ascontiguousarray(rng.uniform(0, 8, size=(300, 3)).astype(np.float32).astype(np.float64))
+    vals = np.ascontiguousarray(rng.normal(size=(300, 3)))
+    ax = [np.linspace(0, 7, 8), np.linspace(0, 6, 7), np.linspace(0, 5, 6)]
+    out = np.zeros((3, 6, 7, 8), dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.ptv_interpolate_host(p(pts), p(vals), 300, p(ax[0]), 8, p(ax[1]), 7, p(ax[2]), 6, None,
+                                  _cabi.METHOD_IDW, 12, 2.0, 0.0, _cabi.F32, p(out[0]), p(out[1]), p(out[2]))
+    _cabi.check(rc)
+    Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+    Ur, Vr, Wr = rp.interpolate_field(pts, vals, (X, Y, Z), method="idw", idw_neighbors=12)
+    _assert_vel(out, np.stack([Ur, Vr, Wr]), vals)
+    rc = lib.ptv_interpolate_host(p(pts), p(vals), 5, p(ax[0]), 8, p(ax[1]), 7, p(ax[2]), 6, None,
+                                  _cabi.METHOD_IDW, 12, 2.0, 0.0, _cabi.F32, p(out[0]), p(out[1]), p(out[2]))
+    assert rc == _cabi.PTV_ERR_TOO_FEW and b"out of bounds" in lib.ptv_last_error()
