@@ -338,6 +338,8 @@ extern "C" int ptv_hash_create(ptv_hash** out) {
   ptv_hash* h = new ptv_hash();
   cudaError_t e = cudaMalloc(&h->bbox_dev, (kBboxBlocks * 7 + 8) * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost(&h->bbox_host, 8 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->err_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->err_host, sizeof(int));
   if (e != cudaSuccess) {
     cudaFree(h->bbox_dev);
     delete h;
@@ -352,7 +354,9 @@ extern "C" int ptv_hash_destroy(ptv_hash* h) {
   cudaFree(h->rec); cudaFree(h->vals); cudaFree(h->cid); cudaFree(h->sorted_idx);
   cudaFree(h->cell_start); cudaFree(h->cell_fill); cudaFree(h->scan_tmp);
   cudaFree(h->bbox_dev);
+  cudaFree(h->err_flag);
   if (h->bbox_host) cudaFreeHost(h->bbox_host);
+  if (h->err_host) cudaFreeHost(h->err_host);
   delete h;
   return PTV_OK;
 }

@@ -37,6 +37,8 @@ struct KnnParams {
   double* knn_dist;
   int tiles_x, tiles_y, tiles_z;
   int r0;
+  double smoothing;
+  int* err_flag;
 };
 
 __device__ __forceinline__ bool key_greater(double ka, int ia, double kb, int ib) {
@@ -104,7 +106,163 @@ __device__ __forceinline__ void store_out(void* base, int64_t i, double v) {
   reinterpret_cast<OutT*>(base)[i] = (OutT)v;
 }
 
-template <int T, int TX, int TY, int TZ, typename OutT>
+
+// ------------------------------------------------------------------------------------------
+// Local RBF (interpolator.py:157-195 -> scipy RBFInterpolator(neighbors=k), thin-plate spline,
+// degree-1 polynomial tail; scipy/interpolate/_rbfinterp_xp.py:139-266).  Per voxel the
+// (k+4)x(k+4) saddle-point system [[K + sI, P], [P^T, 0]] c = [d; 0] is built and solved in float64
+// by the voxel's warp: lane = matrix row, matrix in shared memory (row stride 33 doubles, bank
+// conflict free), Gaussian elimination with partial pivoting (the system is symmetric indefinite,
+// so no Cholesky; scipy uses LAPACK dsysv), then vec(x) . c with vec = [phi(|x-y_j|), 1, xh, yh, zh].
+static constexpr int kRbfMaxN = 32;                                   // k + 4 <= 32
+static constexpr int kRbfLd = kRbfMaxN + 1;
+static constexpr int kRbfScratchDoubles = kRbfMaxN * kRbfLd + kRbfMaxN * 3 + kRbfMaxN * 3 + kRbfMaxN / 2;
+
+__device__ __forceinline__ double tps_phi_from_d2(double d2) {
+  // phi(r) = r^2 log r with phi(0) = 0 (_rbfinterp_xp.py:98-100); r^2 log r == 0.5 * d2 * log(d2)
+  return d2 > 0.0 ? 0.5 * d2 * log(d2) : 0.0;
+}
+
+template <int T>
+__device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratch, const double* hkey_all,
+                                 const int* hidx_all, double qx, double qy, double qz, bool active, double& su,
+                                 double& sv, double& sw) {
+  const unsigned full = 0xffffffffu;
+  const int t = threadIdx.x, lane = t & 31, wbase = t & ~31;
+  const int k = p.k, n = k + 4;
+  double* A = scratch;                       // [32][33]
+  double* B = A + kRbfMaxN * kRbfLd;         // [32][3] right-hand sides -> coefficients
+  double* Y = B + kRbfMaxN * 3;              // [32][3] neighbour coordinates
+  int* perm = reinterpret_cast<int*>(Y + kRbfMaxN * 3);  // [32] pivot row of each column
+  const HashGrid& g = p.g;
+  for (int v = 0; v < 32; ++v) {
+    if (!__shfl_sync(full, active ? 1 : 0, v)) continue;
+    const double vx = __shfl_sync(full, qx, v), vy = __shfl_sync(full, qy, v), vz = __shfl_sync(full, qz, v);
+    // lane j < k owns neighbour j of voxel v
+    double yx = 0.0, yy = 0.0, yz = 0.0, d2q = 0.0;
+    Value4 val; val.u = val.v = val.w = val.pad = 0.0;
+    if (lane < k) {
+      const int pj = hidx_all[lane * T + wbase + v];
+      d2q = hkey_all[lane * T + wbase + v];
+      yx = g.pts[(int64_t)pj * 3 + 0];
+      yy = g.pts[(int64_t)pj * 3 + 1];
+      yz = g.pts[(int64_t)pj * 3 + 2];
+      val = g.vals[pj];
+    }
+    // shift / scale of the neighbourhood (_rbfinterp_xp.py:186-193)
+    double mn[3] = {lane < k ? yx : INFINITY, lane < k ? yy : INFINITY, lane < k ? yz : INFINITY};
+    double mx[3] = {lane < k ? yx : -INFINITY, lane < k ? yy : -INFINITY, lane < k ? yz : -INFINITY};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        mn[c] = fmin(mn[c], __shfl_xor_sync(full, mn[c], o));
+        mx[c] = fmax(mx[c], __shfl_xor_sync(full, mx[c], o));
+      }
+    }
+    double shift[3], scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      shift[c] = (mx[c] + mn[c]) / 2.0;
+      scale[c] = (mx[c] - mn[c]) / 2.0;
+      if (scale[c] == 0.0) scale[c] = 1.0;
+    }
+    if (lane < k) {
+      Y[lane * 3 + 0] = yx; Y[lane * 3 + 1] = yy; Y[lane * 3 + 2] = yz;
+    }
+    __syncwarp();
+    if (lane < k) {
+      double* row = A + lane * kRbfLd;
+      for (int j = 0; j < k; ++j) {
+        const double dx = yx - Y[j * 3 + 0], dy = yy - Y[j * 3 + 1], dz = yz - Y[j * 3 + 2];
+        row[j] = tps_phi_from_d2((dx * dx + dy * dy) + dz * dz);
+      }
+      row[lane] += p.smoothing;
+      row[k + 0] = 1.0;
+      row[k + 1] = (yx - shift[0]) / scale[0];
+      row[k + 2] = (yy - shift[1]) / scale[1];
+      row[k + 3] = (yz - shift[2]) / scale[2];
+      B[lane * 3 + 0] = val.u; B[lane * 3 + 1] = val.v; B[lane * 3 + 2] = val.w;
+    }
+    __syncwarp();
+    if (lane >= k && lane < n) {  // polynomial rows: P^T | 0
+      double* row = A + lane * kRbfLd;
+      for (int j = 0; j < k; ++j) row[j] = A[j * kRbfLd + lane];
+      for (int j = k; j < n; ++j) row[j] = 0.0;
+      B[lane * 3 + 0] = 0.0; B[lane * 3 + 1] = 0.0; B[lane * 3 + 2] = 0.0;
+    }
+    __syncwarp();
+    // ---- elimination with partial pivoting; rows stay in place, perm[col] = pivot row
+    bool used = false;
+    int my_col = n;  // column this row pivots (n = not yet)
+    bool singular = false;
+    for (int c = 0; c < n; ++c) {
+      double bv = (lane < n && !used) ? fabs(A[lane * kRbfLd + c]) : -1.0;
+      int best = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(full, bv, o);
+        const int ol = __shfl_xor_sync(full, best, o);
+        if (ov > bv || (ov == bv && ol < best)) { bv = ov; best = ol; }
+      }
+      if (!(bv > 0.0)) { singular = true; break; }  // exact zero (or NaN) pivot column: dsysv info > 0
+      if (lane == best) { used = true; my_col = c; perm[c] = lane; }
+      const double* prow = A + best * kRbfLd;
+      const double piv = prow[c];
+      if (lane < n && !used) {
+        double* row = A + lane * kRbfLd;
+        const double f = row[c] / piv;
+        if (f != 0.0) {
+          for (int j = c + 1; j < n; ++j) row[j] -= f * prow[j];
+          B[lane * 3 + 0] -= f * B[best * 3 + 0];
+          B[lane * 3 + 1] -= f * B[best * 3 + 1];
+          B[lane * 3 + 2] -= f * B[best * 3 + 2];
+        }
+      }
+      __syncwarp();
+    }
+    if (singular) {
+      if (lane == 0) atomicExch(p.err_flag, 1);
+      __syncwarp();
+      continue;
+    }
+    // ---- back substitution: the row pivoting column c holds unknown c
+    for (int c = n - 1; c >= 0; --c) {
+      const int r = perm[c];
+      const double inv = 1.0 / A[r * kRbfLd + c];
+      const double x0 = B[r * 3 + 0] * inv, x1 = B[r * 3 + 1] * inv, x2 = B[r * 3 + 2] * inv;
+      __syncwarp();
+      if (lane == r) { B[r * 3 + 0] = x0; B[r * 3 + 1] = x1; B[r * 3 + 2] = x2; }
+      if (lane < n && my_col < c) {
+        const double a = A[lane * kRbfLd + c];
+        B[lane * 3 + 0] -= a * x0; B[lane * 3 + 1] -= a * x1; B[lane * 3 + 2] -= a * x2;
+      }
+      __syncwarp();
+    }
+    // ---- evaluate vec(x) . coeffs (_rbfinterp_xp.py:213-266); lane j holds unknown j's weight
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+    if (lane < n) {
+      double vj;
+      if (lane < k) vj = tps_phi_from_d2(d2q);
+      else if (lane == k) vj = 1.0;
+      else if (lane == k + 1) vj = (vx - shift[0]) / scale[0];
+      else if (lane == k + 2) vj = (vy - shift[1]) / scale[1];
+      else vj = (vz - shift[2]) / scale[2];
+      const int r = perm[lane];
+      e0 = vj * B[r * 3 + 0]; e1 = vj * B[r * 3 + 1]; e2 = vj * B[r * 3 + 2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      e0 += __shfl_xor_sync(full, e0, o);
+      e1 += __shfl_xor_sync(full, e1, o);
+      e2 += __shfl_xor_sync(full, e2, o);
+    }
+    if (lane == v) { su = e0; sv = e1; sw = e2; }
+    __syncwarp();
+  }
+}
+
+template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf>
 __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
   static_assert(TX * TY * TZ == T, "tile shape");
   constexpr int NW = T / 32;
@@ -117,6 +275,8 @@ __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
   int* seg_start = hidx_all + (size_t)k * T;                            // [T]
   int* seg_off = seg_start + T;                                         // [T+1]
   int* warp_tot = seg_off + T + 1;                                      // [NW]
+  double* rbf_scratch = reinterpret_cast<double*>(
+      (reinterpret_cast<uintptr_t>(warp_tot + NW) + 15) & ~(uintptr_t)15);  // [NW][kRbfScratchDoubles], RBF only
 
   const int t = threadIdx.x;
   double* hk = hkey_all + t;
@@ -302,6 +462,15 @@ __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
     r += 1;
   }
 
+  const int kk = count;  // == k whenever Np >= k (checked on the host)
+  double su = 0.0, sv = 0.0, sw = 0.0;
+
+  if (kRbf) {
+    // every lane of the warp helps to solve each voxel's local system, so no early exits here
+    rbf_tps_epilogue<T>(p, rbf_scratch + (size_t)(t >> 5) * kRbfScratchDoubles, hkey_all, hidx_all, qx, qy, qz,
+                        active && kk == k, su, sv, sw);
+  }
+
   if (!valid) return;
   if (!active) {
     store_out<OutT>(p.u, vox, 0.0);
@@ -316,7 +485,6 @@ __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
     return;
   }
 
-  const int kk = count;  // == k whenever Np >= k (checked on the host)
   if (kk < k) {
     // heap property was never established; order for the outputs below is fixed by the sort
     for (int h = kk / 2 - 1; h >= 0; --h) sift_down<T>(hk, hi, kk, h, hk[h * T], hi[h * T]);
@@ -337,8 +505,9 @@ __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
     }
   }
 
-  double su = 0.0, sv = 0.0, sw = 0.0;
-  if (p.method == PTV_METHOD_NEAREST || (p.method == PTV_METHOD_IDW && kk == 1)) {
+  if (kRbf) {
+    // computed above
+  } else if (p.method == PTV_METHOD_NEAREST || (p.method == PTV_METHOD_IDW && kk == 1)) {
     // k = 1: the weight cancels; copy the value (griddata 'nearest', interpolator.py:197)
     int best = 0;
     for (int j = 1; j < kk; ++j)
@@ -399,23 +568,25 @@ __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
   store_out<OutT>(p.w, vox, sw);
 }
 
-static size_t knn_smem_bytes(int T, int k) {
+static size_t knn_smem_bytes(int T, int k, int method) {
   const int NW = T / 32;
   size_t b = (size_t)k * T * sizeof(double) + (size_t)kStageCap * sizeof(ParticleRec) +
              (size_t)6 * NW * sizeof(double) + (size_t)k * T * sizeof(int) +
              (size_t)(2 * T + 1 + NW) * sizeof(int);
+  b = (b + 15) & ~(size_t)15;
+  if (method == PTV_METHOD_RBF) b += 16 + (size_t)NW * kRbfScratchDoubles * sizeof(double);
   return (b + 15) & ~(size_t)15;
 }
 
-template <int T, int TX, int TY, int TZ, typename OutT>
+template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf = false>
 static int launch_knn(KnnParams& p, cudaStream_t stream) {
   p.tiles_x = (p.nx + TX - 1) / TX;
   p.tiles_y = (p.ny + TY - 1) / TY;
   p.tiles_z = (p.nz + TZ - 1) / TZ;
   const int64_t ntiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
   if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
-  const size_t smem = knn_smem_bytes(T, p.k);
-  auto kern = knn_interp_kernel<T, TX, TY, TZ, OutT>;
+  const size_t smem = knn_smem_bytes(T, p.k, p.method);
+  auto kern = knn_interp_kernel<T, TX, TY, TZ, OutT, kRbf>;
   PTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)ntiles, T, smem, stream>>>(p);
   count_launches(1);
@@ -431,15 +602,27 @@ extern "C" int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, c
                               const double* d_ax_z, int nz, const uint8_t* d_mask, int method, int k,
                               double idw_power, double rbf_smoothing, int out_dtype, void* d_u, void* d_v,
                               void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream_) {
-  (void)rbf_smoothing;
   if (!h || !h->built) { set_error("ptv_knn_interp: hash not built"); return PTV_ERR_INVALID; }
   if (!d_ax_x || !d_ax_y || !d_ax_z || !d_u || !d_v || !d_w) { set_error("ptv_knn_interp: NULL argument"); return PTV_ERR_INVALID; }
   if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_knn_interp: empty grid"); return PTV_ERR_INVALID; }
   if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_interp: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
   if (method == PTV_METHOD_NEAREST) k = 1;
-  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST) {
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST &&
+      method != PTV_METHOD_RBF) {
     set_error("ptv_knn_interp: unsupported method");
     return PTV_ERR_INVALID;
+  }
+  if (method == PTV_METHOD_RBF) {
+    if ((int64_t)k > h->n) k = (int)h->n;  // RBFInterpolator clamps neighbors to Np (scipy _rbfinterp.py:313)
+    if (k < 4) {
+      set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3.");
+      return PTV_ERR_INVALID;
+    }
+    if (k + 4 > 32) {
+      set_error("ptv_knn_interp: rbf_neighbors > 28 is not supported on the CUDA path");
+      return PTV_ERR_INVALID;
+    }
+    if (!(rbf_smoothing >= 0.0)) { set_error("ptv_knn_interp: smoothing must be >= 0"); return PTV_ERR_INVALID; }
   }
   if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_interp: bad out_dtype"); return PTV_ERR_INVALID; }
   if (k < 1) { set_error("ptv_knn_interp: k must be >= 1"); return PTV_ERR_INVALID; }
@@ -457,19 +640,33 @@ extern "C" int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, c
   p.u = d_u; p.v = d_v; p.w = d_w;
   p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
   p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
+  p.smoothing = rbf_smoothing;
+  p.err_flag = h->err_flag;
+  if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
 
   const size_t smem_max = 227 * 1024;
   int T = tuning().tile;
   if (T != 32 && T != 64 && T != 128) T = 128;
-  while (T > 32 && knn_smem_bytes(T, k) > smem_max / 2) T >>= 1;  // keep >= 2 CTAs per SM if possible
-  if (knn_smem_bytes(T, k) > smem_max) {
+  while (T > 32 && knn_smem_bytes(T, k, method) > smem_max / 2) T >>= 1;  // keep >= 2 CTAs per SM if possible
+  if (knn_smem_bytes(T, k, method) > smem_max) {
     set_error("ptv_knn_interp: k too large for shared memory (max ~580)");
     return PTV_ERR_INVALID;
   }
   const bool f32 = out_dtype == PTV_F32;
-  switch (T) {
-    case 128: return f32 ? launch_knn<128, 8, 4, 4, float>(p, stream) : launch_knn<128, 8, 4, 4, double>(p, stream);
-    case 64: return f32 ? launch_knn<64, 4, 4, 4, float>(p, stream) : launch_knn<64, 4, 4, 4, double>(p, stream);
-    default: return f32 ? launch_knn<32, 4, 4, 2, float>(p, stream) : launch_knn<32, 4, 4, 2, double>(p, stream);
+  int rc;
+  if (method == PTV_METHOD_RBF) {
+    rc = f32 ? launch_knn<128, 8, 4, 4, float, true>(p, stream) : launch_knn<128, 8, 4, 4, double, true>(p, stream);
+  } else switch (T) {
+    case 128: rc = f32 ? launch_knn<128, 8, 4, 4, float>(p, stream) : launch_knn<128, 8, 4, 4, double>(p, stream); break;
+    case 64: rc = f32 ? launch_knn<64, 4, 4, 4, float>(p, stream) : launch_knn<64, 4, 4, 4, double>(p, stream); break;
+    default: rc = f32 ? launch_knn<32, 4, 4, 2, float>(p, stream) : launch_knn<32, 4, 4, 2, double>(p, stream); break;
   }
+  if (rc != PTV_OK) return rc;
+  if (method == PTV_METHOD_RBF) {
+    // a singular neighbourhood must surface as LinAlgError like scipy's dsysv info > 0 check
+    PTV_CUDA(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PTV_CUDA(cudaStreamSynchronize(stream));
+    if (*h->err_host != 0) { set_error("Singular matrix."); return PTV_ERR_SINGULAR; }
+  }
+  return PTV_OK;
 }

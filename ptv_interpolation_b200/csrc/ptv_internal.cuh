@@ -62,6 +62,8 @@ struct ptv_hash {
   int32_t* scan_tmp = nullptr;
   double* bbox_dev = nullptr;     // 6 doubles + scratch partials
   double* bbox_host = nullptr;    // pinned, 8 doubles
+  int* err_flag = nullptr;        // device, RBF singularity flag
+  int* err_host = nullptr;        // pinned
   int64_t cap_n = 0;
   int64_t cap_cells = 0;
   int64_t cap_scan = 0;

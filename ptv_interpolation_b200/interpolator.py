@@ -116,7 +116,7 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     if method == "rbf":
         k = min(int(k), len(points))  # scipy _rbfinterp.py:313 clamps silently
     eng.build(pts, vals)
-    ax = [torch.from_numpy(a).to(dev) for a in (x, y, z)]
+    ax = [torch.from_numpy(np.array(a, dtype=np.float64)).to(dev) for a in (x, y, z)]
     m = None
     if mask is not None:
         m = torch.from_numpy(np.ascontiguousarray(mask).astype(np.uint8, copy=False)).to(dev)

@@ -267,3 +267,51 @@ def test_host_cabi_entry_point():
     rc = lib.ptv_interpolate_host(p(pts), p(vals), 5, p(ax[0]), 8, p(ax[1]), 7, p(ax[2]), 6, None,
                                   _cabi.METHOD_IDW, 12, 2.0, 0.0, _cabi.F32, p(out[0]), p(out[1]), p(out[2]))
     assert rc == _cabi.PTV_ERR_TOO_FEW and b"out of bounds" in lib.ptv_last_error()
+
+
+# ------------------------------------------------------------------ local RBF (a8/a9)
+@pytest.mark.parametrize("name,kw", [("rbf_k20", dict(method="rbf")),
+                                     ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1))])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_golden_rbf(case_a, name, kw, dtype):
+    g, grid, df = case_a
+    U, V, W = gi.interpolate_field(df, grid, out_dtype=dtype, **kw)
+    _assert_vel(np.stack([U, V, W]), g[name], g["values"])
+    if dtype == np.float64:
+        err = np.abs(np.stack([U, V, W]) - g[name]).max()
+        print(f"rbf {name}: max abs err vs scipy dsysv {err:.3e}")
+
+
+def test_rbf_reference_own_test(golden_dir):
+    """test_parallel.py:6-27: 5 points, rbf with n_jobs=2 (accepted, ignored); neighbours clamp to Np."""
+    g = np.load(os.path.join(golden_dir, "case_e_test_parallel.npz"))
+    df = pd.DataFrame({"x": [0, 10, 0, 10, 5], "y": [0, 0, 10, 10, 5], "z": [0, 0, 0, 0, 5],
+                       "u": [1, 1, 1, 1, 2], "v": [0, 0, 0, 0, 0], "w": [0, 0, 0, 0, 0]})
+    grid, _ = gi.create_grid(((0, 10), (0, 10), (0, 10)), 10)
+    U, V, W = gi.interpolate_field(df, grid, method="rbf", n_jobs=2, out_dtype=np.float64)
+    assert U.shape == (10, 10, 10)
+    vals = df[["u", "v", "w"]].values.astype(float)
+    vals[:, 1:] = 1.0  # rms scale for the all-zero components
+    _assert_vel(np.stack([U, V, W]), g["uvw"], vals)
+
+
+def test_rbf_sphere_pack_vs_oracle_and_errors():
+    n = 24
+    mask = synthetic.hex6_sphere_pack_mask(n)
+    pts = synthetic.sample_pore_particles(mask, 2500, seed=21)
+    vals = synthetic.sphere_pack_flow(pts, n)
+    pts, vals, mask = pts.numpy(), vals.numpy(), mask.numpy()
+    b = ((0, n), (0, n), (0, n))
+    grid, _ = gi.create_grid(b, n)
+    U, V, W = gi.interpolate_field(_df(pts, vals), grid, method="rbf", mask=mask, out_dtype=np.float64)
+    og, _ = rp.create_grid(b, n)
+    Ur, Vr, Wr = rp.interpolate_field(pts, vals, og, method="rbf")
+    ref = np.stack(rp.apply_mask_zero(Ur, Vr, Wr, mask))
+    _assert_vel(np.stack([U, V, W]), ref, vals)
+    # coplanar neighbourhood: exactly singular saddle-point system -> LinAlgError like scipy
+    flat = pts[:300].copy()
+    flat[:, 2] = 3.0
+    with pytest.raises(np.linalg.LinAlgError):
+        gi.interpolate_field(_df(flat, vals[:300]), grid, method="rbf")
+    with pytest.raises(ValueError):  # fewer than 4 points: RBFInterpolator raises ValueError
+        gi.interpolate_field(_df(pts[:3], vals[:3]), grid, method="rbf")
