@@ -55,7 +55,8 @@ const char* ptv_last_error(void);
 /* sm count, compute capability and memory of `device`; fails with PTV_ERR_CUDA if absent. */
 int ptv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 /* Tuning knobs for experiments ("ppc" particles per cell, "r0" rings merged into the first
- * staging batch, "tile" 64|128|256 threads per voxel tile).  Unknown key -> PTV_ERR_INVALID. */
+ * staging batch, "tile" / "stream_tile" 32|64|128 threads per voxel tile of the heap / streaming
+ * kernel, "stream" 0|1 use the streaming kernel, "stats" 0|1).  Unknown key -> PTV_ERR_INVALID. */
 int ptv_set_tuning(const char* key, double value);
 /* Number of CUDA kernels this library has launched in this process so far (bench.py's
  * gpu_launches is the difference across the timed region). */
@@ -86,6 +87,11 @@ int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, const double
                    const double* d_ax_z, int nz, const uint8_t* d_mask, int method, int k,
                    double idw_power, double rbf_smoothing, int out_dtype, void* d_u, void* d_v,
                    void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream);
+
+/* Diagnostics of the last ptv_knn_interp call on this handle: whether the streaming kernel ran,
+ * how many voxel tiles it handed to the exact heap kernel, and (with tuning "stats" = 1) how many it
+ * finished itself.  Synchronises the device. */
+int ptv_knn_stats(const ptv_hash* h, int64_t* used_stream, int64_t* tiles_failed, int64_t* tiles_streamed);
 
 /* ---- mask resampling: replaces sample_mask_on_grid (interpolator.py:205-238).  The
  *      per-axis nearest index maps (-1 == out of bounds) are computed by the host shim with

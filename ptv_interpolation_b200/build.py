@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptvb200.so")
-SOURCES = ["cabi.cu", "hash_build.cu", "knn_interp.cu", "grid_ops.cu"]
-HEADERS = [os.path.join(CSRC, "ptv_internal.cuh"), os.path.join(ROOT, "include", "ptv_b200.h")]
+SOURCES = ["cabi.cu", "hash_build.cu", "knn_interp.cu", "knn_stream.cu", "knn_dispatch.cu", "grid_ops.cu"]
+HEADERS = [os.path.join(CSRC, "ptv_internal.cuh"), os.path.join(CSRC, "knn_common.cuh"), os.path.join(ROOT, "include", "ptv_b200.h")]
 
 
 def nvcc_path() -> str:

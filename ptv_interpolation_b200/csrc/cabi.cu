@@ -53,6 +53,9 @@ extern "C" int ptv_set_tuning(const char* key, double value) {
   if (!strcmp(key, "ppc")) { if (!(value > 0)) { set_error("ppc must be > 0"); return PTV_ERR_INVALID; } t.ppc = value; }
   else if (!strcmp(key, "r0")) t.r0 = (int)value;
   else if (!strcmp(key, "tile")) t.tile = (int)value;
+  else if (!strcmp(key, "stream")) t.stream = (int)value;
+  else if (!strcmp(key, "stream_tile")) t.stream_tile = (int)value;
+  else if (!strcmp(key, "stats")) t.stats = (int)value;
   else { set_error(std::string("ptv_set_tuning: unknown key ") + key); return PTV_ERR_INVALID; }
   return PTV_OK;
 }
@@ -63,6 +66,9 @@ extern "C" double ptv_get_tuning(const char* key) {
   if (!strcmp(key, "ppc")) return t.ppc;
   if (!strcmp(key, "r0")) return t.r0;
   if (!strcmp(key, "tile")) return t.tile;
+  if (!strcmp(key, "stream")) return t.stream;
+  if (!strcmp(key, "stream_tile")) return t.stream_tile;
+  if (!strcmp(key, "stats")) return t.stats;
   return nan("");
 }
 

@@ -355,6 +355,8 @@ extern "C" int ptv_hash_destroy(ptv_hash* h) {
   cudaFree(h->cell_start); cudaFree(h->cell_fill); cudaFree(h->scan_tmp);
   cudaFree(h->bbox_dev);
   cudaFree(h->err_flag);
+  cudaFree(h->fail_list);
+  cudaFree(h->fail_count);
   if (h->bbox_host) cudaFreeHost(h->bbox_host);
   if (h->err_host) cudaFreeHost(h->err_host);
   delete h;

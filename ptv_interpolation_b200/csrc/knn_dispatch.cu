@@ -1,0 +1,130 @@
+// ptv_knn_interp: argument checks and the choice between the streaming kernel (IDW / sibson,
+// k >= 8, no neighbour-list output) with its exact heap-kernel fallback, and the heap kernel alone.
+#include <string>
+
+#include "knn_common.cuh"
+
+using namespace ptv;
+
+static int ensure_fail_buffers(ptv_hash* h, int64_t ntiles) {
+  if (h->fail_cap < ntiles) {
+    cudaFree(h->fail_list);
+    h->fail_list = nullptr;
+    h->fail_cap = 0;
+    PTV_CUDA(cudaMalloc(&h->fail_list, (size_t)(ntiles + 1024) * sizeof(int)));
+    h->fail_cap = ntiles + 1024;
+  }
+  if (h->fail_count == nullptr) PTV_CUDA(cudaMalloc(&h->fail_count, 4 * sizeof(unsigned long long)));
+  return PTV_OK;
+}
+
+static void tile_shape(int T, int& tx, int& ty, int& tz) {
+  tx = T == 128 ? 8 : 4; ty = 4; tz = T == 32 ? 2 : 4;
+}
+
+extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, const double* d_ax_y, int ny,
+                              const double* d_ax_z, int nz, const uint8_t* d_mask, int method, int k,
+                              double idw_power, double rbf_smoothing, int out_dtype, void* d_u, void* d_v,
+                              void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream_) {
+  ptv_hash* h = const_cast<ptv_hash*>(hc);  // scratch buffers of the handle are grown on demand
+  if (!h || !h->built) { set_error("ptv_knn_interp: hash not built"); return PTV_ERR_INVALID; }
+  if (!d_ax_x || !d_ax_y || !d_ax_z || !d_u || !d_v || !d_w) { set_error("ptv_knn_interp: NULL argument"); return PTV_ERR_INVALID; }
+  if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_knn_interp: empty grid"); return PTV_ERR_INVALID; }
+  if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_interp: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
+  if (method == PTV_METHOD_NEAREST) k = 1;
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST &&
+      method != PTV_METHOD_RBF) {
+    set_error("ptv_knn_interp: unsupported method");
+    return PTV_ERR_INVALID;
+  }
+  if (method == PTV_METHOD_RBF) {
+    if ((int64_t)k > h->n) k = (int)h->n;  // RBFInterpolator clamps neighbors to Np (scipy _rbfinterp.py:313)
+    if (k < 4) {
+      set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3.");
+      return PTV_ERR_INVALID;
+    }
+    if (k + 4 > 32) {
+      set_error("ptv_knn_interp: rbf_neighbors > 28 is not supported on the CUDA path");
+      return PTV_ERR_INVALID;
+    }
+    if (!(rbf_smoothing >= 0.0)) { set_error("ptv_knn_interp: smoothing must be >= 0"); return PTV_ERR_INVALID; }
+  }
+  if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_interp: bad out_dtype"); return PTV_ERR_INVALID; }
+  if (k < 1) { set_error("ptv_knn_interp: k must be >= 1"); return PTV_ERR_INVALID; }
+  if ((int64_t)k > h->n) {
+    // values[indices] with index == Np: IndexError in the reference (interpolator.py:150)
+    set_error("index " + std::to_string(h->n) + " is out of bounds for axis 0 with size " + std::to_string(h->n));
+    return PTV_ERR_TOO_FEW;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KnnParams p;
+  p.g = h->view();
+  p.ax = d_ax_x; p.ay = d_ax_y; p.az = d_ax_z;
+  p.nx = nx; p.ny = ny; p.nz = nz;
+  p.mask = d_mask; p.method = method; p.k = k; p.power = idw_power;
+  p.u = d_u; p.v = d_v; p.w = d_w;
+  p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
+  p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
+  p.smoothing = rbf_smoothing;
+  p.err_flag = h->err_flag;
+  p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
+  p.tiles_x = p.tiles_y = p.tiles_z = 0;
+  if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
+
+  const size_t smem_max = 227 * 1024;
+  const bool f32 = out_dtype == PTV_F32;
+  const bool use_stream = tuning().stream != 0 && (method == PTV_METHOD_IDW || method == PTV_METHOD_SIBSON) &&
+                          k >= 8 && d_knn_idx == nullptr;
+  int T = use_stream ? tuning().stream_tile : tuning().tile;
+  if (T != 32 && T != 64 && T != 128) T = 128;
+  if (use_stream) {
+    while (T > 32 && knn_heap_smem_bytes(T, k, method) > smem_max) T >>= 1;  // the fallback must fit
+  } else {
+    while (T > 32 && knn_heap_smem_bytes(T, k, method) > smem_max / 2) T >>= 1;  // >= 2 CTAs per SM if possible
+  }
+  if (knn_heap_smem_bytes(T, k, method) > smem_max) {
+    set_error("ptv_knn_interp: k too large for shared memory (max ~580)");
+    return PTV_ERR_INVALID;
+  }
+  h->last_used_stream = use_stream;
+  int rc;
+  if (use_stream) {
+    int tx, ty, tz;
+    tile_shape(T, tx, ty, tz);
+    const int64_t ntiles = (int64_t)((nx + tx - 1) / tx) * ((ny + ty - 1) / ty) * ((nz + tz - 1) / tz);
+    if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
+    rc = ensure_fail_buffers(h, ntiles);
+    if (rc != PTV_OK) return rc;
+    PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, 4 * sizeof(unsigned long long), stream));
+    p.fail_list = h->fail_list;
+    p.fail_count = reinterpret_cast<int*>(h->fail_count);
+    p.stats = tuning().stats != 0 ? h->fail_count + 1 : nullptr;
+    rc = launch_knn_stream(p, T, f32, stream);
+    if (rc != PTV_OK) return rc;
+    // exact heap kernel over whatever the optimistic kernel could not finish
+    p.tile_list = h->fail_list;
+    p.tile_count = reinterpret_cast<const int*>(h->fail_count);
+    rc = launch_knn_heap(p, T, f32, stream);
+  } else {
+    rc = launch_knn_heap(p, T, f32, stream);
+  }
+  if (rc != PTV_OK) return rc;
+  if (method == PTV_METHOD_RBF) {
+    // a singular neighbourhood must surface as LinAlgError like scipy's dsysv info > 0 check
+    PTV_CUDA(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PTV_CUDA(cudaStreamSynchronize(stream));
+    if (*h->err_host != 0) { set_error("Singular matrix."); return PTV_ERR_SINGULAR; }
+  }
+  return PTV_OK;
+}
+
+extern "C" int ptv_knn_stats(const ptv_hash* h, int64_t* used_stream, int64_t* tiles_failed, int64_t* tiles_streamed) {
+  if (!h) { set_error("ptv_knn_stats: NULL handle"); return PTV_ERR_INVALID; }
+  if (used_stream) *used_stream = h->last_used_stream ? 1 : 0;
+  unsigned long long host[2] = {0, 0};
+  if (h->last_used_stream && h->fail_count != nullptr)
+    PTV_CUDA(cudaMemcpy(host, h->fail_count, sizeof(host), cudaMemcpyDeviceToHost));
+  if (tiles_failed) *tiles_failed = (int64_t)(host[0] & 0xffffffffULL);
+  if (tiles_streamed) *tiles_streamed = (int64_t)host[1];
+  return PTV_OK;
+}

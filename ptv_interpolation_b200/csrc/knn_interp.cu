@@ -12,38 +12,9 @@
 // Exactness: d2 = (dx*dx + dy*dy) + dz*dz in float64 with no FMA contraction, ordering is
 // (d2, original index) -- the same total order as the canonicalised oracle -- so the selected
 // neighbour SET and its sorted order are bit-exact regardless of staging order.
-#include <math.h>
-
-#include "ptv_internal.cuh"
+#include "knn_common.cuh"
 
 namespace ptv {
-
-static constexpr int kStageCap = 256;  // particle records per staging chunk (8 KB)
-
-struct KnnParams {
-  HashGrid g;
-  const double* ax;
-  const double* ay;
-  const double* az;
-  int nx, ny, nz;
-  const uint8_t* mask;
-  int method;
-  int k;
-  double power;
-  void* u;
-  void* v;
-  void* w;
-  int64_t* knn_idx;
-  double* knn_dist;
-  int tiles_x, tiles_y, tiles_z;
-  int r0;
-  double smoothing;
-  int* err_flag;
-};
-
-__device__ __forceinline__ bool key_greater(double ka, int ia, double kb, int ib) {
-  return ka > kb || (ka == kb && ia > ib);
-}
 
 // Place (nk, ni) at `pos` of the size-n max-heap and sift it down.  Column `t` of [slot][T].
 template <int T>
@@ -71,41 +42,6 @@ __device__ __forceinline__ void sift_down(double* __restrict__ hk, int* __restri
   hk[pos * T] = nk;
   hi[pos * T] = ni;
 }
-
-template <int T>
-__device__ __forceinline__ int block_scan_excl(int v, int* warp_tot, int* total) {
-  constexpr int NW = T / 32;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int x = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += x;
-  }
-  if (lane == 31) warp_tot[wid] = inc;
-  __syncthreads();
-  int woff = 0, tot = 0;
-#pragma unroll
-  for (int w2 = 0; w2 < NW; ++w2) {
-    const int x = warp_tot[w2];
-    if (w2 < wid) woff += x;
-    tot += x;
-  }
-  __syncthreads();
-  *total = tot;
-  return woff + inc - v;
-}
-
-__device__ __forceinline__ int cell_of(double p, double o, double inv_cell, int n) {
-  const int c = (int)floor((p - o) * inv_cell);
-  return min(max(c, 0), n - 1);
-}
-
-template <typename OutT>
-__device__ __forceinline__ void store_out(void* base, int64_t i, double v) {
-  reinterpret_cast<OutT*>(base)[i] = (OutT)v;
-}
-
 
 // ------------------------------------------------------------------------------------------
 // Local RBF (interpolator.py:157-195 -> scipy RBFInterpolator(neighbors=k), thin-plate spline,
@@ -263,10 +199,9 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
 }
 
 template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf>
-__global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
+__device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, unsigned char* smem_raw) {
   static_assert(TX * TY * TZ == T, "tile shape");
   constexpr int NW = T / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = p.k;
   double* hkey_all = reinterpret_cast<double*>(smem_raw);               // [k][T]
   ParticleRec* stage = reinterpret_cast<ParticleRec*>(hkey_all + (size_t)k * T);  // [kStageCap]
@@ -283,7 +218,6 @@ __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
   int* hi = hidx_all + t;
 
   const HashGrid& g = p.g;
-  const int tile = blockIdx.x;
   const int tx = tile % p.tiles_x;
   const int ty = (tile / p.tiles_x) % p.tiles_y;
   const int tz = tile / (p.tiles_x * p.tiles_y);
@@ -568,7 +502,24 @@ __global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
   store_out<OutT>(p.w, vox, sw);
 }
 
-static size_t knn_smem_bytes(int T, int k, int method) {
+// One CTA per tile, or -- when the streaming kernel handed over a fail list -- a fixed grid of CTAs
+// striding over the listed tiles.
+template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf>
+__global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (p.tile_list == nullptr) {
+    heap_tile<T, TX, TY, TZ, OutT, kRbf>(p, (int)blockIdx.x, smem_raw);
+  } else {
+    const int n = *p.tile_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+      heap_tile<T, TX, TY, TZ, OutT, kRbf>(p, p.tile_list[i], smem_raw);
+      __syncthreads();
+    }
+  }
+}
+
+
+size_t knn_heap_smem_bytes(int T, int k, int method) {
   const int NW = T / 32;
   size_t b = (size_t)k * T * sizeof(double) + (size_t)kStageCap * sizeof(ParticleRec) +
              (size_t)6 * NW * sizeof(double) + (size_t)k * T * sizeof(int) +
@@ -585,88 +536,25 @@ static int launch_knn(KnnParams& p, cudaStream_t stream) {
   p.tiles_z = (p.nz + TZ - 1) / TZ;
   const int64_t ntiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
   if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
-  const size_t smem = knn_smem_bytes(T, p.k, p.method);
+  const size_t smem = knn_heap_smem_bytes(T, p.k, p.method);
   auto kern = knn_interp_kernel<T, TX, TY, TZ, OutT, kRbf>;
   PTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)ntiles, T, smem, stream>>>(p);
+  // fail-list mode: a few CTAs per SM stride over the listed tiles (the count lives on the device)
+  const int64_t grid = p.tile_list != nullptr ? (ntiles < 148 * 4 ? ntiles : 148 * 4) : ntiles;
+  kern<<<(unsigned)grid, T, smem, stream>>>(p);
   count_launches(1);
   PTV_CUDA(cudaGetLastError());
   return PTV_OK;
 }
 
-}  // namespace ptv
-
-using namespace ptv;
-
-extern "C" int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, const double* d_ax_y, int ny,
-                              const double* d_ax_z, int nz, const uint8_t* d_mask, int method, int k,
-                              double idw_power, double rbf_smoothing, int out_dtype, void* d_u, void* d_v,
-                              void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream_) {
-  if (!h || !h->built) { set_error("ptv_knn_interp: hash not built"); return PTV_ERR_INVALID; }
-  if (!d_ax_x || !d_ax_y || !d_ax_z || !d_u || !d_v || !d_w) { set_error("ptv_knn_interp: NULL argument"); return PTV_ERR_INVALID; }
-  if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_knn_interp: empty grid"); return PTV_ERR_INVALID; }
-  if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_interp: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
-  if (method == PTV_METHOD_NEAREST) k = 1;
-  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST &&
-      method != PTV_METHOD_RBF) {
-    set_error("ptv_knn_interp: unsupported method");
-    return PTV_ERR_INVALID;
+int launch_knn_heap(KnnParams& p, int T, bool f32, cudaStream_t stream) {
+  if (p.method == PTV_METHOD_RBF)
+    return f32 ? launch_knn<128, 8, 4, 4, float, true>(p, stream) : launch_knn<128, 8, 4, 4, double, true>(p, stream);
+  switch (T) {
+    case 128: return f32 ? launch_knn<128, 8, 4, 4, float>(p, stream) : launch_knn<128, 8, 4, 4, double>(p, stream);
+    case 64: return f32 ? launch_knn<64, 4, 4, 4, float>(p, stream) : launch_knn<64, 4, 4, 4, double>(p, stream);
+    default: return f32 ? launch_knn<32, 4, 4, 2, float>(p, stream) : launch_knn<32, 4, 4, 2, double>(p, stream);
   }
-  if (method == PTV_METHOD_RBF) {
-    if ((int64_t)k > h->n) k = (int)h->n;  // RBFInterpolator clamps neighbors to Np (scipy _rbfinterp.py:313)
-    if (k < 4) {
-      set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3.");
-      return PTV_ERR_INVALID;
-    }
-    if (k + 4 > 32) {
-      set_error("ptv_knn_interp: rbf_neighbors > 28 is not supported on the CUDA path");
-      return PTV_ERR_INVALID;
-    }
-    if (!(rbf_smoothing >= 0.0)) { set_error("ptv_knn_interp: smoothing must be >= 0"); return PTV_ERR_INVALID; }
-  }
-  if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_interp: bad out_dtype"); return PTV_ERR_INVALID; }
-  if (k < 1) { set_error("ptv_knn_interp: k must be >= 1"); return PTV_ERR_INVALID; }
-  if ((int64_t)k > h->n) {
-    // values[indices] with index == Np: IndexError in the reference (interpolator.py:150)
-    set_error("index " + std::to_string(h->n) + " is out of bounds for axis 0 with size " + std::to_string(h->n));
-    return PTV_ERR_TOO_FEW;
-  }
-  cudaStream_t stream = (cudaStream_t)stream_;
-  KnnParams p;
-  p.g = h->view();
-  p.ax = d_ax_x; p.ay = d_ax_y; p.az = d_ax_z;
-  p.nx = nx; p.ny = ny; p.nz = nz;
-  p.mask = d_mask; p.method = method; p.k = k; p.power = idw_power;
-  p.u = d_u; p.v = d_v; p.w = d_w;
-  p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
-  p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
-  p.smoothing = rbf_smoothing;
-  p.err_flag = h->err_flag;
-  if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
-
-  const size_t smem_max = 227 * 1024;
-  int T = tuning().tile;
-  if (T != 32 && T != 64 && T != 128) T = 128;
-  while (T > 32 && knn_smem_bytes(T, k, method) > smem_max / 2) T >>= 1;  // keep >= 2 CTAs per SM if possible
-  if (knn_smem_bytes(T, k, method) > smem_max) {
-    set_error("ptv_knn_interp: k too large for shared memory (max ~580)");
-    return PTV_ERR_INVALID;
-  }
-  const bool f32 = out_dtype == PTV_F32;
-  int rc;
-  if (method == PTV_METHOD_RBF) {
-    rc = f32 ? launch_knn<128, 8, 4, 4, float, true>(p, stream) : launch_knn<128, 8, 4, 4, double, true>(p, stream);
-  } else switch (T) {
-    case 128: rc = f32 ? launch_knn<128, 8, 4, 4, float>(p, stream) : launch_knn<128, 8, 4, 4, double>(p, stream); break;
-    case 64: rc = f32 ? launch_knn<64, 4, 4, 4, float>(p, stream) : launch_knn<64, 4, 4, 4, double>(p, stream); break;
-    default: rc = f32 ? launch_knn<32, 4, 4, 2, float>(p, stream) : launch_knn<32, 4, 4, 2, double>(p, stream); break;
-  }
-  if (rc != PTV_OK) return rc;
-  if (method == PTV_METHOD_RBF) {
-    // a singular neighbourhood must surface as LinAlgError like scipy's dsysv info > 0 check
-    PTV_CUDA(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    PTV_CUDA(cudaStreamSynchronize(stream));
-    if (*h->err_host != 0) { set_error("Singular matrix."); return PTV_ERR_SINGULAR; }
-  }
-  return PTV_OK;
 }
+
+}  // namespace ptv

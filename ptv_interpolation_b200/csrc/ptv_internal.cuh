@@ -38,7 +38,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 struct Tuning {
   double ppc = 1.0;  // target particles per cell
   int r0 = 1;        // rings merged into the first staging batch
-  int tile = 128;    // threads (= voxels) per tile
+  int tile = 128;    // threads (= voxels) per tile, heap kernel
+  int stream = 1;    // 1 = streaming kernel for idw/sibson with k >= 8 (heap kernel as fallback)
+  int stream_tile = 128;
+  int stats = 0;     // 1 = count streamed tiles
 };
 Tuning& tuning();
 void count_launches(int n);
@@ -64,6 +67,10 @@ struct ptv_hash {
   double* bbox_host = nullptr;    // pinned, 8 doubles
   int* err_flag = nullptr;        // device, RBF singularity flag
   int* err_host = nullptr;        // pinned
+  int* fail_list = nullptr;       // tiles handed from the streaming to the heap kernel
+  int64_t fail_cap = 0;
+  unsigned long long* fail_count = nullptr;  // [0] low 32 bits: fail count; [1]: streamed tiles (stats)
+  bool last_used_stream = false;
   int64_t cap_n = 0;
   int64_t cap_cells = 0;
   int64_t cap_scan = 0;

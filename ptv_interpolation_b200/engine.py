@@ -127,6 +127,13 @@ class PTVEngine:
             return out, kd, ki
         return out
 
+    def knn_stats(self):
+        """Diagnostics of the last interpolate(): did the streaming kernel run, how many tiles fell
+        back to the exact heap kernel, how many it finished itself (needs set_tuning(stats=1))."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _cabi.check(self.lib.ptv_knn_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"used_stream": bool(a.value), "tiles_failed": b.value, "tiles_streamed": c.value}
+
     # ------------------------------------------------------------------ grid ops
     def mask_gather(self, mask_raw, ix, iy, iz):
         rnz, rny, rnx = mask_raw.shape

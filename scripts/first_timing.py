@@ -21,7 +21,7 @@ def main():
         ax = torch.linspace(0, n - 1, n, dtype=torch.float64, device=dev)
         pore = int(cfg["mask"].sum())
         for var in variants:
-            set_tuning(tile=128, r0=1, ppc=1.0)
+            set_tuning(tile=128, r0=1, ppc=1.0, stream=1, stream_tile=128, stats=0)
             set_tuning(**var)
             for masked in (True, False):
                 if not masked and n > 512:
@@ -38,9 +38,13 @@ def main():
                     torch.cuda.synchronize()
                     ts.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
                 tb, ti = min(t[0] for t in ts), min(t[1] for t in ts)
+                set_tuning(stats=1)
+                eng.interpolate(ax, ax, ax, mask=mask if masked else None, method=cfg["method"], k=cfg["k"])
+                st = eng.knn_stats()
+                set_tuning(stats=0)
                 nv = pore if masked else n ** 3
                 print(f"{name} {var} masked={masked}: build {tb:.2f} ms, interp {ti:.1f} ms, "
-                      f"{nv / ti / 1e3:.1f} Mvox/s ({'pore' if masked else 'all'}), info {eng.hash_info()}", flush=True)
+                      f"{nv / ti / 1e3:.1f} Mvox/s ({'pore' if masked else 'all'}), stats {st}", flush=True)
                 del out
 
 

@@ -193,6 +193,67 @@ def test_tuning_does_not_change_neighbours(case_a, tune):
     assert np.array_equal(ki, g["knn_i_k50"]) and np.array_equal(kd, g["knn_d_k50"])
 
 
+def _stream_vs_heap(df, grid, mask=None, **kw):
+    """float64 outputs of the streaming kernel and of the exact heap kernel: the neighbour SETS are
+    identical iff the weighted means agree to summation-order rounding."""
+    from ptv_interpolation_b200.engine import default_engine
+    try:
+        set_tuning(stream=1, stats=1)
+        a = np.stack(gi.interpolate_field(df, grid, mask=mask, out_dtype=np.float64, **kw))
+        st = default_engine().knn_stats()
+        set_tuning(stream=0)
+        b = np.stack(gi.interpolate_field(df, grid, mask=mask, out_dtype=np.float64, **kw))
+        assert not default_engine().knn_stats()["used_stream"]
+    finally:
+        set_tuning(stream=1, stats=0)
+    assert st["used_stream"]
+    scale = np.abs(b).max()
+    assert np.abs(a - b).max() <= 1e-11 * scale, float(np.abs(a - b).max() / scale)
+    return a, st
+
+
+@pytest.mark.parametrize("tune", [dict(), dict(stream_tile=64), dict(stream_tile=32), dict(r0=0), dict(r0=2),
+                                  dict(ppc=0.4), dict(ppc=5.0)])
+@pytest.mark.parametrize("kw", [dict(method="idw"), dict(method="idw", idw_neighbors=9, idw_power=3.0),
+                                dict(method="sibson"), dict(method="sibson", sibson_neighbors=50)])
+def test_stream_kernel_matches_heap_kernel(case_a, tune, kw):
+    g, grid, df = case_a
+    try:
+        set_tuning(**tune)
+        _stream_vs_heap(df, grid, **kw)
+    finally:
+        set_tuning(stream_tile=128, r0=1, ppc=1.0)
+
+
+def test_stream_kernel_sphere_pack_and_fallback_paths():
+    n = 48
+    mask = synthetic.hex6_sphere_pack_mask(n)
+    pts = synthetic.sample_pore_particles(mask, 12000, seed=5)
+    vals = synthetic.sphere_pack_flow(pts, n)
+    pts, vals, mask = pts.numpy(), vals.numpy(), mask.numpy()
+    grid, _ = gi.create_grid(((0, n), (0, n), (0, n)), n)
+    # pore voxels only: nearly every tile stays on the streaming kernel
+    a, st = _stream_vs_heap(_df(pts, vals), grid, mask=mask, method="idw")
+    assert st["tiles_streamed"] > 0 and st["tiles_failed"] < 0.2 * (st["tiles_streamed"] + st["tiles_failed"])
+    # all voxels: tiles deep inside the grains have no local density estimate -> heap fallback
+    b, st2 = _stream_vs_heap(_df(pts, vals), grid, method="idw")
+    assert st2["tiles_failed"] > 0
+    assert np.abs(a[:, mask] - b[:, mask]).max() <= 1e-11 * np.abs(b).max()
+    # lattice + exact duplicates + a pile of coincident points: tie groups overflow the short list
+    rng = np.random.default_rng(8)
+    lat = np.stack(np.meshgrid(np.arange(10.0), np.arange(10.0), np.arange(10.0), indexing="ij"), -1).reshape(-1, 3)
+    cloud = np.concatenate([lat, lat[:200], np.full((120, 3), 4.5),
+                            rng.uniform(0, 9, size=(500, 3)).astype(np.float32).astype(np.float64)], 0)
+    cv = rng.normal(size=(len(cloud), 3))
+    g2, _ = gi.create_grid(((0, 10), (0, 10), (0, 10)), 10)
+    c, st3 = _stream_vs_heap(_df(cloud, cv), g2, method="idw", idw_neighbors=30)
+    assert st3["tiles_failed"] > 0
+    og, _ = rp.create_grid(((0, 10), (0, 10), (0, 10)), 10)
+    d, i, _ = rp.knn_bruteforce(cloud, rp.flat_coords(og), 30)
+    ref = np.moveaxis(rp.idw_from_knn(d, i, cv).reshape(og[0].shape + (3,)), -1, 0)
+    _assert_vel(c, ref, cv)
+
+
 @pytest.mark.parametrize("k", [64, 130, 300])
 def test_large_k(k):
     rng = np.random.default_rng(k)
