@@ -64,8 +64,8 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_tot, int* total)
 }
 
 __device__ __forceinline__ int cell_of(double p, double o, double inv_cell, int n) {
-  const int c = (int)floor((p - o) * inv_cell);
-  return min(max(c, 0), n - 1);
+  const double c = floor((p - o) * inv_cell);  // clamped in double: p may be far outside the grid
+  return (int)fmin(fmax(c, 0.0), (double)(n - 1));
 }
 
 template <typename OutT>
@@ -74,6 +74,222 @@ __device__ __forceinline__ void store_out(void* base, int64_t i, double v) {
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// Scan geometry shared by both kernels.  A tile scans the cells within distance R of the bounding
+// box of its active voxels ("rounded box": exact per cell row in y/z, sqrt-clipped along x), then
+// grows R and scans only the new shell.  Every particle within R of ANY point of the bounding box
+// lies in a scanned cell, so for a voxel inside the box "k-th distance < R" proves the search is
+// complete -- the same exactness argument as a ring walk, at ~half the scanned volume.
+struct TileGeom {
+  double lo[3], hi[3];  // bounding box of the tile's active voxels
+  double rmax;          // radius at which the whole cell grid is covered
+};
+
+struct RoundRegion {
+  double R, R2;
+  int y0, y1, z0, z1;  // bounding rectangle of rows (cell coordinates)
+};
+
+__device__ __forceinline__ RoundRegion make_region(const HashGrid& g, const TileGeom& tg, double R) {
+  RoundRegion rg;
+  rg.R = R;
+  rg.R2 = R * R;
+  rg.y0 = cell_of(tg.lo[1] - R, g.oy, g.inv_cell, g.cny);
+  rg.y1 = cell_of(tg.hi[1] + R, g.oy, g.inv_cell, g.cny);
+  rg.z0 = cell_of(tg.lo[2] - R, g.oz, g.inv_cell, g.cnz);
+  rg.z1 = cell_of(tg.hi[2] + R, g.oz, g.inv_cell, g.cnz);
+  return rg;
+}
+
+// Cells [xa, xb] of row (cy, cz) within the region; false if the row is farther than R.
+__device__ __forceinline__ bool row_interval(const HashGrid& g, const TileGeom& tg, const RoundRegion& rg, int cy,
+                                             int cz, int& xa, int& xb) {
+  const double ylo = g.oy + cy * g.cell, zlo = g.oz + cz * g.cell;
+  const double dy = fmax(0.0, fmax(ylo - tg.hi[1], tg.lo[1] - (ylo + g.cell)));
+  const double dz = fmax(0.0, fmax(zlo - tg.hi[2], tg.lo[2] - (zlo + g.cell)));
+  const double rem = rg.R2 - (dy * dy + dz * dz);
+  if (rem < 0.0) return false;
+  const double hx = sqrt(rem);
+  xa = cell_of(tg.lo[0] - hx, g.ox, g.inv_cell, g.cnx);
+  xb = cell_of(tg.hi[0] + hx, g.ox, g.inv_cell, g.cnx);
+  return true;
+}
+
+__device__ __forceinline__ int region_slots(const RoundRegion& rg, bool have_prev) {
+  const int nrows = (rg.y1 - rg.y0 + 1) * (rg.z1 - rg.z0 + 1);
+  return have_prev ? 2 * nrows : nrows;
+}
+
+// Record range [start, start+cnt) of slot s of the shell  region(rg) \ region(prev).
+__device__ __forceinline__ void resolve_slot(const HashGrid& g, const TileGeom& tg, const RoundRegion& rg,
+                                             const RoundRegion& prev, bool have_prev, int s, int nslots, int& start,
+                                             int& cnt) {
+  start = 0;
+  cnt = 0;
+  if (s >= nslots) return;
+  const int nrows_y = rg.y1 - rg.y0 + 1;
+  const int row = have_prev ? (s >> 1) : s;
+  const int which = have_prev ? (s & 1) : 0;
+  const int cy = rg.y0 + row % nrows_y;
+  const int cz = rg.z0 + row / nrows_y;
+  int xa, xb;
+  if (!row_interval(g, tg, rg, cy, cz, xa, xb)) return;
+  if (have_prev) {
+    int pa, pb;
+    const bool in_prev = cy >= prev.y0 && cy <= prev.y1 && cz >= prev.z0 && cz <= prev.z1 &&
+                         row_interval(g, tg, prev, cy, cz, pa, pb);
+    if (in_prev) {
+      if (which == 0) xb = pa - 1; else xa = pb + 1;
+    } else if (which == 1) {
+      return;
+    }
+  }
+  if (xa <= xb) {
+    const int64_t rowbase = ((int64_t)cz * g.cny + cy) * g.cnx;
+    start = g.cell_start[rowbase + xa];
+    cnt = g.cell_start[rowbase + xb + 1] - start;
+  }
+}
+
+struct ScanSmem {
+  ParticleRec* stage64;  // [kStageCap] exact records (may be NULL if unused)
+  float4* stage32;       // [kStageCap] tile-centre-relative float32 x,y,z (may be NULL if unused)
+  int* seg_start;        // [T]
+  int* seg_off;          // [T+1]
+  int* warp_tot;         // [NW]
+};
+
+// Stage the shell  region(rg) \ region(prev)  chunk by chunk through shared memory and call body(m)
+// on each staged chunk of m records.  Returns the number of records staged.
+template <int T, bool kWith32, bool kWith64, typename F>
+__device__ __forceinline__ int scan_shell(const HashGrid& g, const TileGeom& tg, const RoundRegion& rg,
+                                          const RoundRegion& prev, bool have_prev, const ScanSmem& sm, double cx,
+                                          double cy, double cz, F&& body) {
+  const int t = threadIdx.x;
+  const int nslots = region_slots(rg, have_prev);
+  int staged = 0;
+  for (int slot_base = 0; slot_base < nslots; slot_base += T) {
+    int start, cnt;
+    resolve_slot(g, tg, rg, prev, have_prev, slot_base + t, nslots, start, cnt);
+    int total;
+    const int off = block_scan_excl<T>(cnt, sm.warp_tot, &total);
+    sm.seg_start[t] = start;
+    sm.seg_off[t] = off;
+    if (t == 0) sm.seg_off[T] = total;
+    __syncthreads();
+    staged += total;
+    for (int chunk0 = 0; chunk0 < total; chunk0 += kStageCap) {
+      const int m = min(kStageCap, total - chunk0);
+      for (int j = t; j < m; j += T) {
+        const int gpos = chunk0 + j;
+        int lo = 0, hi2 = T - 1;
+        while (lo < hi2) {  // record j of the chunk lives in the last segment whose offset <= gpos
+          const int mid = (lo + hi2 + 1) >> 1;
+          if (sm.seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
+        }
+        const ParticleRec* src = g.rec + (sm.seg_start[lo] + (gpos - sm.seg_off[lo]));
+        const int4 a = __ldg(reinterpret_cast<const int4*>(src));
+        const int4 c = __ldg(reinterpret_cast<const int4*>(src) + 1);
+        if (kWith64) {
+          int4* dst = reinterpret_cast<int4*>(sm.stage64 + j);
+          dst[0] = a;
+          dst[1] = c;
+        }
+        if (kWith32) {
+          const double px = __hiloint2double(a.y, a.x), py = __hiloint2double(a.w, a.z);
+          const double pz = __hiloint2double(c.y, c.x);
+          sm.stage32[j] = make_float4((float)(px - cx), (float)(py - cy), (float)(pz - cz), 0.0f);
+        }
+      }
+      __syncthreads();
+      body(m);
+      __syncthreads();
+    }
+  }
+  return staged;
+}
+
+// Bounding box of the tile's active voxels (block reduction through `red`[6*NW]) and the radius
+// that covers the whole cell grid.
+template <int T>
+__device__ __forceinline__ void tile_geometry(const HashGrid& g, bool active, double qx, double qy, double qz,
+                                              double* red, TileGeom& tg) {
+  constexpr int NW = T / 32;
+  const int t = threadIdx.x;
+  double v6[6];
+  v6[0] = active ? qx : INFINITY;
+  v6[1] = active ? qy : INFINITY;
+  v6[2] = active ? qz : INFINITY;
+  v6[3] = active ? -qx : INFINITY;
+  v6[4] = active ? -qy : INFINITY;
+  v6[5] = active ? -qz : INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) v6[c] = fmin(v6[c], __shfl_xor_sync(0xffffffffu, v6[c], o));
+  }
+  if ((t & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) red[c * NW + (t >> 5)] = v6[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double a = red[c * NW], b = red[(c + 3) * NW];
+#pragma unroll
+    for (int w2 = 1; w2 < NW; ++w2) {
+      a = fmin(a, red[c * NW + w2]);
+      b = fmin(b, red[(c + 3) * NW + w2]);
+    }
+    tg.lo[c] = a;
+    tg.hi[c] = -b;
+  }
+  const double glo[3] = {g.ox, g.oy, g.oz};
+  const double ghi[3] = {g.ox + g.cnx * g.cell, g.oy + g.cny * g.cell, g.oz + g.cnz * g.cell};
+  double r2 = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double m = fmax(fmax(tg.hi[c] - glo[c], ghi[c] - tg.lo[c]), 0.0);
+    r2 += m * m;
+  }
+  tg.rmax = sqrt(r2) * (1.0 + 1e-9) + 1e-3 * g.cell;
+}
+
+// Particles in the cells overlapping the tile's box widened by r0 cells -> local density -> the
+// radius expected to hold k particles.  Returns r_est (or a negative value if fewer than
+// `min_count` particles are nearby and no estimate can be made).
+template <int T>
+__device__ __forceinline__ double estimate_radius(const HashGrid& g, const TileGeom& tg, int r0, int k, int min_count,
+                                                  int* warp_tot) {
+  const int t = threadIdx.x;
+  int r = max(r0, 0);
+  for (int attempt = 0;; ++attempt) {
+    int b0[3], b1[3];
+    b0[0] = max(cell_of(tg.lo[0], g.ox, g.inv_cell, g.cnx) - r, 0);
+    b1[0] = min(cell_of(tg.hi[0], g.ox, g.inv_cell, g.cnx) + r, g.cnx - 1);
+    b0[1] = max(cell_of(tg.lo[1], g.oy, g.inv_cell, g.cny) - r, 0);
+    b1[1] = min(cell_of(tg.hi[1], g.oy, g.inv_cell, g.cny) + r, g.cny - 1);
+    b0[2] = max(cell_of(tg.lo[2], g.oz, g.inv_cell, g.cnz) - r, 0);
+    b1[2] = min(cell_of(tg.hi[2], g.oz, g.inv_cell, g.cnz) + r, g.cnz - 1);
+    const int nry = b1[1] - b0[1] + 1, nrows = nry * (b1[2] - b0[2] + 1);
+    int mine = 0;
+    for (int s = t; s < nrows; s += T) {
+      const int64_t rowbase = ((int64_t)(b0[2] + s / nry) * g.cny + (b0[1] + s % nry)) * g.cnx;
+      mine += g.cell_start[rowbase + b1[0] + 1] - g.cell_start[rowbase + b0[0]];
+    }
+    int n1;
+    (void)block_scan_excl<T>(mine, warp_tot, &n1);
+    const bool whole = b0[0] == 0 && b0[1] == 0 && b0[2] == 0 && b1[0] == g.cnx - 1 && b1[1] == g.cny - 1 &&
+                       b1[2] == g.cnz - 1;
+    if (n1 >= min_count) {
+      const double vol = (double)(b1[0] - b0[0] + 1) * nry * (b1[2] - b0[2] + 1) * g.cell * g.cell * g.cell;
+      return cbrt(0.238732414637843 * k * vol / n1);  // (3k / (4 pi rho))^(1/3)
+    }
+    if (attempt >= 3 || whole) return -1.0;
+    r += 1;
+  }
+}
 
 // launchers defined next to their kernels
 int launch_knn_heap(KnnParams& p, int T, bool f32, cudaStream_t stream);

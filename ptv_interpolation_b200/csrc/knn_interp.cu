@@ -247,153 +247,60 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
   const double qy = valid ? p.ay[iy] : 0.0;
   const double qz = valid ? p.az[iz] : 0.0;
 
-  // ---- bounding box of the tile's active voxels -> cell range of ring 0
-  {
-    double v6[6];
-    v6[0] = active ? qx : INFINITY;
-    v6[1] = active ? qy : INFINITY;
-    v6[2] = active ? qz : INFINITY;
-    v6[3] = active ? -qx : INFINITY;
-    v6[4] = active ? -qy : INFINITY;
-    v6[5] = active ? -qz : INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) v6[c] = fmin(v6[c], __shfl_xor_sync(0xffffffffu, v6[c], o));
-    }
-    if ((t & 31) == 0) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) red[c * NW + (t >> 5)] = v6[c];
-    }
-  }
-  __syncthreads();
-  double bb[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    double a = red[c * NW];
-#pragma unroll
-    for (int w2 = 1; w2 < NW; ++w2) a = fmin(a, red[c * NW + w2]);
-    bb[c] = a;
-  }
-  const int c0x = cell_of(bb[0], g.ox, g.inv_cell, g.cnx);
-  const int c0y = cell_of(bb[1], g.oy, g.inv_cell, g.cny);
-  const int c0z = cell_of(bb[2], g.oz, g.inv_cell, g.cnz);
-  const int c1x = cell_of(-bb[3], g.ox, g.inv_cell, g.cnx);
-  const int c1y = cell_of(-bb[4], g.oy, g.inv_cell, g.cny);
-  const int c1z = cell_of(-bb[5], g.oz, g.inv_cell, g.cnz);
+  TileGeom tg;
+  tile_geometry<T>(g, active, qx, qy, qz, red, tg);
+  const ScanSmem sm{stage, nullptr, seg_start, seg_off, warp_tot};
 
   int count = 0;
   double thr = INFINITY;  // k-th best d2 once the heap is full
   int root_idx = 0x7fffffff;
 
+  // first radius from the local particle density, then geometric growth until every voxel's k-th
+  // neighbour is provably inside the scanned region
+  const double r_est = estimate_radius<T>(g, tg, p.r0, k, 16, warp_tot);
+  double R = r_est > 0.0 ? 1.15 * r_est : 2.0 * g.cell;
+  RoundRegion prev = make_region(g, tg, 0.0);
   bool have_prev = false;
-  int pbx0 = 0, pbx1 = -1, pby0 = 0, pby1 = -1, pbz0 = 0, pbz1 = -1;
-  int r = p.r0;
   for (;;) {
-    const int bx0 = max(c0x - r, 0), bx1 = min(c1x + r, g.cnx - 1);
-    const int by0 = max(c0y - r, 0), by1 = min(c1y + r, g.cny - 1);
-    const int bz0 = max(c0z - r, 0), bz1 = min(c1z + r, g.cnz - 1);
-    if (have_prev && bx0 == pbx0 && bx1 == pbx1 && by0 == pby0 && by1 == pby1 && bz0 == pbz0 &&
-        bz1 == pbz1)
-      break;  // the whole cell grid has been scanned
-    const int nrows_y = by1 - by0 + 1;
-    const int nrows = nrows_y * (bz1 - bz0 + 1);
-    const int nslots = have_prev ? 2 * nrows : nrows;
-
-    for (int slot_base = 0; slot_base < nslots; slot_base += T) {
-      // ---- each thread resolves one row segment of the shell to a contiguous record range
-      const int s = slot_base + t;
-      int start = 0, cnt = 0;
-      if (s < nslots) {
-        const int row = have_prev ? (s >> 1) : s;
-        const int which = have_prev ? (s & 1) : 0;
-        const int cy = by0 + row % nrows_y;
-        const int cz = bz0 + row / nrows_y;
-        int xa, xb;  // inclusive cell range along x
-        if (!have_prev || cy < pby0 || cy > pby1 || cz < pbz0 || cz > pbz1) {
-          xa = which == 0 ? bx0 : 1;
-          xb = which == 0 ? bx1 : 0;
-        } else if (which == 0) {
-          xa = bx0;
-          xb = pbx0 - 1;
-        } else {
-          xa = pbx1 + 1;
-          xb = bx1;
-        }
-        if (xa <= xb) {
-          const int64_t rowbase = ((int64_t)cz * g.cny + cy) * g.cnx;
-          start = g.cell_start[rowbase + xa];
-          cnt = g.cell_start[rowbase + xb + 1] - start;
-        }
-      }
-      int total;
-      const int off = block_scan_excl<T>(cnt, warp_tot, &total);
-      seg_start[t] = start;
-      seg_off[t] = off;
-      if (t == 0) seg_off[T] = total;
-      __syncthreads();
-
-      for (int chunk0 = 0; chunk0 < total; chunk0 += kStageCap) {
-        const int m = min(kStageCap, total - chunk0);
-        // ---- stage: record j of the chunk lives in the last segment whose offset <= j
-        for (int j = t; j < m; j += T) {
-          const int gpos = chunk0 + j;
-          int lo = 0, hi2 = T - 1;
-          while (lo < hi2) {
-            const int mid = (lo + hi2 + 1) >> 1;
-            if (seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
-          }
-          const int4* src = reinterpret_cast<const int4*>(g.rec + (seg_start[lo] + (gpos - seg_off[lo])));
-          int4* dst = reinterpret_cast<int4*>(stage + j);
-          dst[0] = __ldg(src);
-          dst[1] = __ldg(src + 1);
-        }
-        __syncthreads();
-        // ---- scan: every active thread tests every staged particle
-        if (active) {
+    const bool last = R >= tg.rmax;
+    if (last) R = tg.rmax;
+    const RoundRegion rg = make_region(g, tg, R);
+    scan_shell<T, false, true>(g, tg, rg, prev, have_prev, sm, 0.0, 0.0, 0.0, [&](int m) {
+      if (active) {
 #pragma unroll 2
-          for (int j = 0; j < m; ++j) {
-            const double2 xy = *reinterpret_cast<const double2*>(&stage[j].x);
-            const double zz = stage[j].z;
-            const int pidx = stage[j].idx;
-            const double dx = qx - xy.x, dy = qy - xy.y, dz = qz - zz;
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (d2 < thr || (d2 == thr && pidx < root_idx)) {
-              if (count < k) {
-                hk[count * T] = d2;
-                hi[count * T] = pidx;
-                ++count;
-                if (count == k) {
-                  for (int h = k / 2 - 1; h >= 0; --h) sift_down<T>(hk, hi, k, h, hk[h * T], hi[h * T]);
-                  thr = hk[0];
-                  root_idx = hi[0];
-                }
-              } else {
-                sift_down<T>(hk, hi, k, 0, d2, pidx);
+        for (int j = 0; j < m; ++j) {
+          const double2 xy = *reinterpret_cast<const double2*>(&stage[j].x);
+          const double zz = stage[j].z;
+          const int pidx = stage[j].idx;
+          const double dx = qx - xy.x, dy = qy - xy.y, dz = qz - zz;
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          if (d2 < thr || (d2 == thr && pidx < root_idx)) {
+            if (count < k) {
+              hk[count * T] = d2;
+              hi[count * T] = pidx;
+              ++count;
+              if (count == k) {
+                for (int h = k / 2 - 1; h >= 0; --h) sift_down<T>(hk, hi, k, h, hk[h * T], hi[h * T]);
                 thr = hk[0];
                 root_idx = hi[0];
               }
+            } else {
+              sift_down<T>(hk, hi, k, 0, d2, pidx);
+              thr = hk[0];
+              root_idx = hi[0];
             }
           }
         }
-        __syncthreads();
       }
-    }
-
-    // ---- exact termination: the k-th distance must be inside the scanned box
-    double gap = INFINITY;
-    if (bx0 > 0) gap = fmin(gap, qx - (g.ox + bx0 * g.cell));
-    if (bx1 < g.cnx - 1) gap = fmin(gap, (g.ox + (bx1 + 1) * g.cell) - qx);
-    if (by0 > 0) gap = fmin(gap, qy - (g.oy + by0 * g.cell));
-    if (by1 < g.cny - 1) gap = fmin(gap, (g.oy + (by1 + 1) * g.cell) - qy);
-    if (bz0 > 0) gap = fmin(gap, qz - (g.oz + bz0 * g.cell));
-    if (bz1 < g.cnz - 1) gap = fmin(gap, (g.oz + (bz1 + 1) * g.cell) - qz);
-    gap -= 1e-6 * g.cell;  // absorbs rounding in the particle -> cell assignment
-    const bool done = !active || (count >= k && gap > 0.0 && thr < gap * gap);
-    if (__syncthreads_and(done ? 1 : 0)) break;
+    });
+    // exact termination: the k-th distance must be inside the scanned region (margin absorbs
+    // rounding in the particle -> cell assignment)
+    const double reff = R - 1e-6 * g.cell;
+    const bool done = !active || (count >= k && thr < reff * reff);
+    if (__syncthreads_and(done ? 1 : 0) || last) break;
+    prev = rg;
     have_prev = true;
-    pbx0 = bx0; pbx1 = bx1; pby0 = by0; pby1 = by1; pbz0 = bz0; pbz1 = bz1;
-    r += 1;
+    R *= 1.25;
   }
 
   const int kk = count;  // == k whenever Np >= k (checked on the host)
@@ -505,7 +412,7 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
 // One CTA per tile, or -- when the streaming kernel handed over a fail list -- a fixed grid of CTAs
 // striding over the listed tiles.
 template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf>
-__global__ void __launch_bounds__(T) knn_interp_kernel(const KnnParams p) {
+__global__ void __launch_bounds__(T, 2) knn_interp_kernel(const KnnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (p.tile_list == nullptr) {
     heap_tile<T, TX, TY, TZ, OutT, kRbf>(p, (int)blockIdx.x, smem_raw);

@@ -27,102 +27,6 @@ static constexpr int kNB = 32;        // histogram bins over [0, Tmax)
 static constexpr int kListCap = 20;   // capacity of the crossing-bin list
 static constexpr int kMinEstimate = 16;
 
-struct Box {
-  int x0, x1, y0, y1, z0, z1;
-  __device__ bool operator==(const Box& o) const {
-    return x0 == o.x0 && x1 == o.x1 && y0 == o.y0 && y1 == o.y1 && z0 == o.z0 && z1 == o.z1;
-  }
-};
-
-__device__ __forceinline__ Box make_box(const int c0[3], const int c1[3], int r, const HashGrid& g) {
-  Box b;
-  b.x0 = max(c0[0] - r, 0); b.x1 = min(c1[0] + r, g.cnx - 1);
-  b.y0 = max(c0[1] - r, 0); b.y1 = min(c1[1] + r, g.cny - 1);
-  b.z0 = max(c0[2] - r, 0); b.z1 = min(c1[2] + r, g.cnz - 1);
-  return b;
-}
-
-// Record range [start, start+cnt) of slot s of the shell  box \ prev  (prev ignored if !have_prev).
-__device__ __forceinline__ void resolve_slot(const HashGrid& g, const Box& b, const Box& pb, bool have_prev, int s,
-                                             int nslots, int& start, int& cnt) {
-  start = 0;
-  cnt = 0;
-  if (s >= nslots) return;
-  const int nrows_y = b.y1 - b.y0 + 1;
-  const int row = have_prev ? (s >> 1) : s;
-  const int which = have_prev ? (s & 1) : 0;
-  const int cy = b.y0 + row % nrows_y;
-  const int cz = b.z0 + row / nrows_y;
-  int xa, xb;
-  if (!have_prev || cy < pb.y0 || cy > pb.y1 || cz < pb.z0 || cz > pb.z1) {
-    xa = which == 0 ? b.x0 : 1;
-    xb = which == 0 ? b.x1 : 0;
-  } else if (which == 0) {
-    xa = b.x0;
-    xb = pb.x0 - 1;
-  } else {
-    xa = pb.x1 + 1;
-    xb = b.x1;
-  }
-  if (xa <= xb) {
-    const int64_t rowbase = ((int64_t)cz * g.cny + cy) * g.cnx;
-    start = g.cell_start[rowbase + xa];
-    cnt = g.cell_start[rowbase + xb + 1] - start;
-  }
-}
-
-struct StreamSmem {
-  float4* stage32;       // [kStageCap] tile-centre-relative float32 x,y,z (+ unused)
-  ParticleRec* stage64;  // [kStageCap] exact records
-  int* seg_start;        // [T]
-  int* seg_off;          // [T+1]
-  int* warp_tot;         // [NW]
-};
-
-// Stage the shell  box \ prev  chunk by chunk and call body(m) on each staged chunk of m records.
-template <int T, bool kWith64, typename F>
-__device__ __forceinline__ void scan_shell(const HashGrid& g, const Box& b, const Box& pb, bool have_prev,
-                                           const StreamSmem& sm, double cx, double cy, double cz, F&& body) {
-  const int t = threadIdx.x;
-  const int nrows = (b.y1 - b.y0 + 1) * (b.z1 - b.z0 + 1);
-  const int nslots = have_prev ? 2 * nrows : nrows;
-  for (int slot_base = 0; slot_base < nslots; slot_base += T) {
-    int start, cnt;
-    resolve_slot(g, b, pb, have_prev, slot_base + t, nslots, start, cnt);
-    int total;
-    const int off = block_scan_excl<T>(cnt, sm.warp_tot, &total);
-    sm.seg_start[t] = start;
-    sm.seg_off[t] = off;
-    if (t == 0) sm.seg_off[T] = total;
-    __syncthreads();
-    for (int chunk0 = 0; chunk0 < total; chunk0 += kStageCap) {
-      const int m = min(kStageCap, total - chunk0);
-      for (int j = t; j < m; j += T) {
-        const int gpos = chunk0 + j;
-        int lo = 0, hi2 = T - 1;
-        while (lo < hi2) {
-          const int mid = (lo + hi2 + 1) >> 1;
-          if (sm.seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
-        }
-        const ParticleRec* src = g.rec + (sm.seg_start[lo] + (gpos - sm.seg_off[lo]));
-        const int4 a = __ldg(reinterpret_cast<const int4*>(src));
-        const int4 c = __ldg(reinterpret_cast<const int4*>(src) + 1);
-        if (kWith64) {
-          int4* dst = reinterpret_cast<int4*>(sm.stage64 + j);
-          dst[0] = a;
-          dst[1] = c;
-        }
-        const double px = __hiloint2double(a.y, a.x), py = __hiloint2double(a.w, a.z);
-        const double pz = __hiloint2double(c.y, c.x);
-        sm.stage32[j] = make_float4((float)(px - cx), (float)(py - cy), (float)(pz - cz), 0.0f);
-      }
-      __syncthreads();
-      body(m);
-      __syncthreads();
-    }
-  }
-}
-
 template <int T, int TX, int TY, int TZ, typename OutT>
 __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   static_assert(TX * TY * TZ == T, "tile shape");
@@ -139,7 +43,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   int* seg_start = reinterpret_cast<int*>(red + 6 * NW);
   int* seg_off = seg_start + T;
   int* warp_tot = seg_off + T + 1;
-  StreamSmem sm{stage32, stage64, seg_start, seg_off, warp_tot};
+  const ScanSmem sm{stage64, stage32, seg_start, seg_off, warp_tot};
 
   const int t = threadIdx.x;
   const int k = p.k;
@@ -167,84 +71,35 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   const double qy = valid ? p.ay[iy] : 0.0;
   const double qz = valid ? p.az[iz] : 0.0;
 
-  // ---- bounding box of the tile's active voxels -> cell range of ring 0, tile centre
-  {
-    double v6[6];
-    v6[0] = active ? qx : INFINITY;
-    v6[1] = active ? qy : INFINITY;
-    v6[2] = active ? qz : INFINITY;
-    v6[3] = active ? -qx : INFINITY;
-    v6[4] = active ? -qy : INFINITY;
-    v6[5] = active ? -qz : INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) v6[c] = fmin(v6[c], __shfl_xor_sync(0xffffffffu, v6[c], o));
-    }
-    if ((t & 31) == 0) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) red[c * NW + (t >> 5)] = v6[c];
-    }
-  }
-  __syncthreads();
-  double bb[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    double a = red[c * NW];
-#pragma unroll
-    for (int w2 = 1; w2 < NW; ++w2) a = fmin(a, red[c * NW + w2]);
-    bb[c] = a;
-  }
-  int c0[3], c1[3];
-  c0[0] = cell_of(bb[0], g.ox, g.inv_cell, g.cnx);
-  c0[1] = cell_of(bb[1], g.oy, g.inv_cell, g.cny);
-  c0[2] = cell_of(bb[2], g.oz, g.inv_cell, g.cnz);
-  c1[0] = cell_of(-bb[3], g.ox, g.inv_cell, g.cnx);
-  c1[1] = cell_of(-bb[4], g.oy, g.inv_cell, g.cny);
-  c1[2] = cell_of(-bb[5], g.oz, g.inv_cell, g.cnz);
-  const double cx = 0.5 * (bb[0] - bb[3]), cy = 0.5 * (bb[1] - bb[4]), cz = 0.5 * (bb[2] - bb[5]);
+  TileGeom tg;
+  tile_geometry<T>(g, active, qx, qy, qz, red, tg);
+  const double cx = 0.5 * (tg.lo[0] + tg.hi[0]), cy = 0.5 * (tg.lo[1] + tg.hi[1]), cz = 0.5 * (tg.lo[2] + tg.hi[2]);
   const float qfx = (float)(qx - cx), qfy = (float)(qy - cy), qfz = (float)(qz - cz);
 
-  // ---- local density -> histogram scale.  N1 = particles in the first box (cell-start lookups only)
-  int r = max(p.r0, 0);
-  Box box = make_box(c0, c1, r, g);
-  int n1 = 0;
-  for (int attempt = 0;; ++attempt) {
-    const int nrows = (box.y1 - box.y0 + 1) * (box.z1 - box.z0 + 1);
-    int mine = 0;
-    for (int s = t; s < nrows; s += T) {
-      int start, cnt;
-      resolve_slot(g, box, box, false, s, nrows, start, cnt);
-      mine += cnt;
-    }
-    int total;
-    (void)block_scan_excl<T>(mine, warp_tot, &total);
-    n1 = total;
-    if (n1 >= kMinEstimate || attempt >= 3) break;
-    const Box nb = make_box(c0, c1, r + 1, g);
-    if (nb == box) break;
-    box = nb;
-    r += 1;
-  }
-  if (n1 < kMinEstimate) {  // nothing to estimate a scale from (deep void / tiny cloud): exact kernel
+  // ---- local density -> radius schedule and histogram scale
+  const double r_est = estimate_radius<T>(g, tg, p.r0, k, kMinEstimate, warp_tot);
+  if (!(r_est > 0.0)) {  // nothing to estimate a scale from (deep void / tiny cloud): exact kernel
     if (t == 0) p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
     return;
   }
-  const double vol = (double)(box.x1 - box.x0 + 1) * (box.y1 - box.y0 + 1) * (box.z1 - box.z0 + 1) * g.cell * g.cell *
-                     g.cell;
-  const double r_est2 = pow(0.238732414637843 * k * vol / n1, 2.0 / 3.0);  // (3k / (4 pi rho))^(2/3)
-  const double tmax = 2.5 * r_est2;
-  const double binw = tmax / kNB;
+  // three scan radii whose squares sit just above histogram bin edges 12, 20 and 32 (= Tmax)
+  const double binw = 1.3 * r_est * r_est / 12.0;
   const float inv_w = (float)(1.0 / binw);
+  constexpr int kEdges[3] = {12, 20, kNB};
 
-  // ---- phase A: ring walk with float32 histogram
+  // ---- phase A: grow the scanned region, float32 histogram of squared distances
   int* hist = hist_all + t;
 #pragma unroll
   for (int b = 0; b < kNB; ++b) hist[b * T] = 0;
-  Box prev = box;
-  bool have_prev = false;
-  for (;;) {
-    scan_shell<T, false>(g, box, prev, have_prev, sm, cx, cy, cz, [&](int m) {
+  RoundRegion prev = make_region(g, tg, 0.0);
+  RoundRegion rg = prev;
+  bool have_prev = false, finished = false;
+  for (int stage = 0; stage < 3; ++stage) {
+    double R = sqrt((kEdges[stage] + 0.02) * binw) + 1e-6 * g.cell;
+    const bool last = R >= tg.rmax;
+    if (last) R = tg.rmax;
+    rg = make_region(g, tg, R);
+    scan_shell<T, true, false>(g, tg, rg, prev, have_prev, sm, cx, cy, cz, [&](int m) {
       if (active) {
 #pragma unroll 4
         for (int j = 0; j < m; ++j) {
@@ -256,34 +111,22 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
         }
       }
     });
-    // exact stop test, conservative in float32: >= k particles in bins entirely below the nearest
-    // unscanned face
-    double gap = INFINITY;
-    if (box.x0 > 0) gap = fmin(gap, qx - (g.ox + box.x0 * g.cell));
-    if (box.x1 < g.cnx - 1) gap = fmin(gap, (g.ox + (box.x1 + 1) * g.cell) - qx);
-    if (box.y0 > 0) gap = fmin(gap, qy - (g.oy + box.y0 * g.cell));
-    if (box.y1 < g.cny - 1) gap = fmin(gap, (g.oy + (box.y1 + 1) * g.cell) - qy);
-    if (box.z0 > 0) gap = fmin(gap, qz - (g.oz + box.z0 * g.cell));
-    if (box.z1 < g.cnz - 1) gap = fmin(gap, (g.oz + (box.z1 + 1) * g.cell) - qz);
-    gap -= 1e-6 * g.cell;
+    // stop test: >= k particles in bins that lie entirely inside the scanned radius (bins below
+    // kEdges[stage]; float32 binning errors are far smaller than the 0.02-bin margin)
     bool done = true;
-    if (active) {
-      done = false;
-      if (gap > 0.0) {
-        const double gl = gap * gap * (1.0 - 1e-3);
-        const int nfull = gl >= tmax ? kNB - 1 : min(kNB - 1, (int)(gl / binw));  // bins [0, nfull) lie below gl
-        int cum = 0;
-        for (int b = 0; b < nfull; ++b) cum += hist[b * T];
-        done = cum >= k;
-      }
+    if (active && !last) {
+      int cum = 0;
+      const int nfull = min(kEdges[stage], kNB - 1);
+      for (int b = 0; b < nfull; ++b) cum += hist[b * T];
+      done = cum >= k;
     }
-    if (__syncthreads_and(done ? 1 : 0)) break;
-    const Box nb = make_box(c0, c1, r + 1, g);
-    if (nb == box) break;  // the whole cell grid has been scanned
-    prev = box;
+    if (__syncthreads_and(done ? 1 : 0) || last) { finished = true; break; }
+    prev = rg;
     have_prev = true;
-    box = nb;
-    r += 1;
+  }
+  if (!finished) {  // the k-th neighbour is beyond the histogram range for some voxel
+    if (t == 0) p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+    return;
   }
 
   // ---- thresholds from the crossing bin
@@ -300,27 +143,20 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
       }
       cum += h;
     }
-    if (bstar < 0) fail = true;  // k-th neighbour beyond the histogram range
+    if (bstar < 0) fail = true;  // crossing in the open-ended last bin
     e_lo = bstar * binw;
     e_hi = (bstar + 1) * binw;
+    // the crossing bin must lie inside the scanned radius unless the whole grid was scanned
+    if (rg.R < tg.rmax && e_hi > (rg.R - 1e-6 * g.cell) * (rg.R - 1e-6 * g.cell)) fail = true;
   }
   if (__syncthreads_or(fail ? 1 : 0)) {
     if (t == 0) p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
     return;
   }
 
-  // ---- phase B: exact classification of the final box
-  // float32 error of d2 relative to the tile centre: coordinates are below `half` in magnitude
-  double half = 0.0;
-  {
-    const double lo[3] = {g.ox + box.x0 * g.cell, g.oy + box.y0 * g.cell, g.oz + box.z0 * g.cell};
-    const double hi[3] = {g.ox + (box.x1 + 1) * g.cell, g.oy + (box.y1 + 1) * g.cell, g.oz + (box.z1 + 1) * g.cell};
-    const double cc[3] = {cx, cy, cz};
-    const double ext[3] = {-(bb[0] + bb[3]), -(bb[1] + bb[4]), -(bb[2] + bb[5])};  // tile extent per axis
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-      half = fmax(half, fmax(fabs(lo[a] - cc[a]), fabs(hi[a] - cc[a])) + ext[a]);
-  }
+  // ---- phase B: exact classification of the final region
+  // float32 error of d2 relative to the tile centre: staged coordinates are below `half` in magnitude
+  const double half = rg.R + fmax(tg.hi[0] - tg.lo[0], fmax(tg.hi[1] - tg.lo[1], tg.hi[2] - tg.lo[2])) + g.cell;
   const double ec = half * 2.4e-7;  // 2 ulp of the largest coordinate
   const float hi32 = (float)((e_hi + 16.0 * sqrt(e_hi) * ec + 64.0 * ec * ec) * (1.0 + 1e-5));
   double* lkey = lkey_all + t;
@@ -332,9 +168,8 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   const bool p2 = p.power == 2.0;
   double wsum = 0.0, su = 0.0, sv = 0.0, sw = 0.0;  // idw accumulators
   double dsum = 0.0, ksum = 0.0;                    // sibson moments: sum d, sum d^2
-  const Box whole = box;
   auto idw_weight = [&](double d2) { return 1.0 / ((p2 ? d2 : pow(sqrt(d2), p.power)) + eps); };
-  scan_shell<T, true>(g, whole, whole, false, sm, cx, cy, cz, [&](int m) {
+  scan_shell<T, true, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
     if (active) {
 #pragma unroll 2
       for (int j = 0; j < m; ++j) {
@@ -428,7 +263,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     if (active)
       for (int i = 0; i < need; ++i) sib_acc(lkey[i * T], lidx[i * T]);
     const float lo32 = (float)((e_lo + 16.0 * sqrt(e_lo) * ec + 64.0 * ec * ec) * (1.0 + 1e-5));
-    scan_shell<T, true>(g, whole, whole, false, sm, cx, cy, cz, [&](int m) {
+    scan_shell<T, true, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
       if (active) {
 #pragma unroll 2
         for (int j = 0; j < m; ++j) {
