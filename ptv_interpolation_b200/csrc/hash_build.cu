@@ -237,8 +237,11 @@ __global__ void __launch_bounds__(256) cell_canonical_kernel(const int32_t* __re
 }
 
 __global__ void __launch_bounds__(256) fill_records_kernel(const double* __restrict__ pts,
+                                                            const double* __restrict__ vals_in,
                                                             const int32_t* __restrict__ sorted_idx,
-                                                            int64_t n, ParticleRec* __restrict__ rec) {
+                                                            int64_t n, ParticleRec* __restrict__ rec,
+                                                            Value4* __restrict__ vals_s64,
+                                                            float4* __restrict__ vals_s32) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int32_t i = sorted_idx[p];
@@ -249,6 +252,13 @@ __global__ void __launch_bounds__(256) fill_records_kernel(const double* __restr
   r.idx = i;
   r.pad = 0;
   rec[p] = r;
+  Value4 v;
+  v.u = vals_in[(int64_t)i * 3 + 0];
+  v.v = vals_in[(int64_t)i * 3 + 1];
+  v.w = vals_in[(int64_t)i * 3 + 2];
+  v.pad = 0.0;
+  vals_s64[p] = v;
+  vals_s32[p] = make_float4((float)v.u, (float)v.v, (float)v.w, 0.0f);
 }
 
 __global__ void __launch_bounds__(256) fill_values_kernel(const double* __restrict__ vals_in, int64_t n,
@@ -267,10 +277,14 @@ static int ensure_capacity(ptv_hash* h, int64_t n, int64_t ncells) {
   if (n > h->cap_n) {
     const int64_t cap = n + n / 8 + 1024;
     cudaFree(h->rec); cudaFree(h->vals); cudaFree(h->cid); cudaFree(h->sorted_idx);
+    cudaFree(h->vals_s64); cudaFree(h->vals_s32);
     h->rec = nullptr; h->vals = nullptr; h->cid = nullptr; h->sorted_idx = nullptr;
+    h->vals_s64 = nullptr; h->vals_s32 = nullptr;
     h->cap_n = 0;
     PTV_CUDA(cudaMalloc(&h->rec, cap * sizeof(ParticleRec)));
     PTV_CUDA(cudaMalloc(&h->vals, cap * sizeof(Value4)));
+    PTV_CUDA(cudaMalloc(&h->vals_s64, cap * sizeof(Value4)));
+    PTV_CUDA(cudaMalloc(&h->vals_s32, cap * sizeof(float4)));
     PTV_CUDA(cudaMalloc(&h->cid, cap * sizeof(int32_t)));
     PTV_CUDA(cudaMalloc(&h->sorted_idx, cap * sizeof(int32_t)));
     h->cap_n = cap;
@@ -323,7 +337,7 @@ using namespace ptv;
 
 ptv::HashGrid ptv_hash::view() const {
   HashGrid g;
-  g.rec = rec; g.cell_start = cell_start; g.vals = vals; g.pts = pts;
+  g.rec = rec; g.cell_start = cell_start; g.vals = vals; g.vals_s64 = vals_s64; g.vals_s32 = vals_s32; g.pts = pts;
   g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
   g.cell = cell; g.inv_cell = 1.0 / cell;
   g.cnx = dims[0]; g.cny = dims[1]; g.cnz = dims[2];
@@ -352,6 +366,7 @@ extern "C" int ptv_hash_create(ptv_hash** out) {
 extern "C" int ptv_hash_destroy(ptv_hash* h) {
   if (!h) return PTV_OK;
   cudaFree(h->rec); cudaFree(h->vals); cudaFree(h->cid); cudaFree(h->sorted_idx);
+  cudaFree(h->vals_s64); cudaFree(h->vals_s32);
   cudaFree(h->cell_start); cudaFree(h->cell_fill); cudaFree(h->scan_tmp);
   cudaFree(h->bbox_dev);
   cudaFree(h->err_flag);
@@ -412,7 +427,7 @@ extern "C" int ptv_hash_build(ptv_hash* h, const double* d_points, const double*
   int32_t* max_count = h->cell_fill + ncells;  // zeroed above
   cell_canonical_kernel<<<(int)((ncells + 255) / 256), 256, 0, stream>>>(h->cell_start, ncells,
                                                                         h->sorted_idx, max_count);
-  fill_records_kernel<<<nb_p, 256, 0, stream>>>(d_points, h->sorted_idx, n, h->rec);
+  fill_records_kernel<<<nb_p, 256, 0, stream>>>(d_points, d_values, h->sorted_idx, n, h->rec, h->vals_s64, h->vals_s32);
   fill_values_kernel<<<nb_p, 256, 0, stream>>>(d_values, n, h->vals);
   count_launches(8);
   PTV_CUDA(cudaGetLastError());

@@ -155,6 +155,7 @@ __device__ __forceinline__ void resolve_slot(const HashGrid& g, const TileGeom& 
 struct ScanSmem {
   ParticleRec* stage64;  // [kStageCap] exact records (may be NULL if unused)
   float4* stage32;       // [kStageCap] tile-centre-relative float32 x,y,z (may be NULL if unused)
+  void* stage_val;       // [kStageCap] float4 (kVal == 1) or Value4 (kVal == 2) values, cell-sorted order
   int* seg_start;        // [T]
   int* seg_off;          // [T+1]
   int* warp_tot;         // [NW]
@@ -162,7 +163,7 @@ struct ScanSmem {
 
 // Stage the shell  region(rg) \ region(prev)  chunk by chunk through shared memory and call body(m)
 // on each staged chunk of m records.  Returns the number of records staged.
-template <int T, bool kWith32, bool kWith64, typename F>
+template <int T, int CAP, bool kWith32, bool kWith64, int kVal, bool kPad32, typename F>
 __device__ __forceinline__ int scan_shell(const HashGrid& g, const TileGeom& tg, const RoundRegion& rg,
                                           const RoundRegion& prev, bool have_prev, const ScanSmem& sm, double cx,
                                           double cy, double cz, F&& body) {
@@ -179,8 +180,8 @@ __device__ __forceinline__ int scan_shell(const HashGrid& g, const TileGeom& tg,
     if (t == 0) sm.seg_off[T] = total;
     __syncthreads();
     staged += total;
-    for (int chunk0 = 0; chunk0 < total; chunk0 += kStageCap) {
-      const int m = min(kStageCap, total - chunk0);
+    for (int chunk0 = 0; chunk0 < total; chunk0 += CAP) {
+      const int m = min(CAP, total - chunk0);
       for (int j = t; j < m; j += T) {
         const int gpos = chunk0 + j;
         int lo = 0, hi2 = T - 1;
@@ -188,7 +189,15 @@ __device__ __forceinline__ int scan_shell(const HashGrid& g, const TileGeom& tg,
           const int mid = (lo + hi2 + 1) >> 1;
           if (sm.seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
         }
-        const ParticleRec* src = g.rec + (sm.seg_start[lo] + (gpos - sm.seg_off[lo]));
+        const int spos = sm.seg_start[lo] + (gpos - sm.seg_off[lo]);
+        const ParticleRec* src = g.rec + spos;
+        if (kVal == 1) reinterpret_cast<float4*>(sm.stage_val)[j] = __ldg(g.vals_s32 + spos);
+        if (kVal == 2) {
+          const int4* vs = reinterpret_cast<const int4*>(g.vals_s64 + spos);
+          int4* vd = reinterpret_cast<int4*>(reinterpret_cast<Value4*>(sm.stage_val) + j);
+          vd[0] = __ldg(vs);
+          vd[1] = __ldg(vs + 1);
+        }
         const int4 a = __ldg(reinterpret_cast<const int4*>(src));
         const int4 c = __ldg(reinterpret_cast<const int4*>(src) + 1);
         if (kWith64) {
@@ -201,6 +210,9 @@ __device__ __forceinline__ int scan_shell(const HashGrid& g, const TileGeom& tg,
           const double pz = __hiloint2double(c.y, c.x);
           sm.stage32[j] = make_float4((float)(px - cx), (float)(py - cy), (float)(pz - cz), 0.0f);
         }
+      }
+      if (kPad32) {  // pad to a multiple of 64 with far-away sentinels so consumers can run fixed trip counts
+        for (int j = m + t; j < ((m + 63) & ~63); j += T) sm.stage32[j] = make_float4(1e30f, 1e30f, 1e30f, 0.0f);
       }
       __syncthreads();
       body(m);

@@ -249,7 +249,7 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
 
   TileGeom tg;
   tile_geometry<T>(g, active, qx, qy, qz, red, tg);
-  const ScanSmem sm{stage, nullptr, seg_start, seg_off, warp_tot};
+  const ScanSmem sm{stage, nullptr, nullptr, seg_start, seg_off, warp_tot};
 
   int count = 0;
   double thr = INFINITY;  // k-th best d2 once the heap is full
@@ -258,14 +258,16 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
   // first radius from the local particle density, then geometric growth until every voxel's k-th
   // neighbour is provably inside the scanned region
   const double r_est = estimate_radius<T>(g, tg, p.r0, k, 16, warp_tot);
-  double R = r_est > 0.0 ? 1.15 * r_est : 2.0 * g.cell;
+  // a first, smaller shell fills the heaps with near particles so later candidates are mostly
+  // rejected by the threshold compare instead of being sifted in
+  double R = r_est > 0.0 ? 0.8 * r_est : 2.0 * g.cell;
   RoundRegion prev = make_region(g, tg, 0.0);
-  bool have_prev = false;
+  bool have_prev = false, had_second = false;
   for (;;) {
     const bool last = R >= tg.rmax;
     if (last) R = tg.rmax;
     const RoundRegion rg = make_region(g, tg, R);
-    scan_shell<T, false, true>(g, tg, rg, prev, have_prev, sm, 0.0, 0.0, 0.0, [&](int m) {
+    scan_shell<T, kStageCap, false, true, 0, false>(g, tg, rg, prev, have_prev, sm, 0.0, 0.0, 0.0, [&](int m) {
       if (active) {
 #pragma unroll 2
         for (int j = 0; j < m; ++j) {
@@ -300,7 +302,8 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
     if (__syncthreads_and(done ? 1 : 0) || last) break;
     prev = rg;
     have_prev = true;
-    R *= 1.25;
+    R *= (!had_second && r_est > 0.0) ? 1.15 / 0.8 : 1.25;
+    had_second = true;
   }
 
   const int kk = count;  // == k whenever Np >= k (checked on the host)

@@ -26,6 +26,25 @@ namespace ptv {
 static constexpr int kNB = 32;        // histogram bins over [0, Tmax)
 static constexpr int kListCap = 20;   // capacity of the crossing-bin list
 static constexpr int kMinEstimate = 16;
+static constexpr int kExactCap = 128;  // chunk size of the exact passes (two 64-bit accept masks)
+
+// Values staged next to the candidates: float32 when the output is float32 (rounding 6e-8 relative,
+// far inside the 1e-5 bar), float64 when the caller asked for float64 output.
+template <typename OutT> struct StageVal;
+template <> struct StageVal<float> {
+  using type = float4;
+  static constexpr int kind = 1;
+  __device__ static float u(const float4& v) { return v.x; }
+  __device__ static float v(const float4& v) { return v.y; }
+  __device__ static float w(const float4& v) { return v.z; }
+};
+template <> struct StageVal<double> {
+  using type = Value4;
+  static constexpr int kind = 2;
+  __device__ static double u(const Value4& v) { return v.u; }
+  __device__ static double v(const Value4& v) { return v.v; }
+  __device__ static double w(const Value4& v) { return v.w; }
+};
 
 template <int T, int TX, int TY, int TZ, typename OutT>
 __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
@@ -39,11 +58,14 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   static_assert(kNB * 4 <= kListCap * 8, "histogram must fit under the list keys");
   ParticleRec* stage64 = reinterpret_cast<ParticleRec*>(lidx_all + (size_t)kListCap * T);
   float4* stage32 = reinterpret_cast<float4*>(stage64 + kStageCap);
-  double* red = reinterpret_cast<double*>(stage32 + kStageCap);                 // [6][NW]
+  using ValT = typename StageVal<OutT>::type;  // float4 for float32 output, Value4 for float64 output
+  constexpr int kVal = StageVal<OutT>::kind;
+  ValT* stage_val = reinterpret_cast<ValT*>(stage32 + kStageCap);
+  double* red = reinterpret_cast<double*>(stage_val + kStageCap);               // [6][NW]
   int* seg_start = reinterpret_cast<int*>(red + 6 * NW);
   int* seg_off = seg_start + T;
   int* warp_tot = seg_off + T + 1;
-  const ScanSmem sm{stage64, stage32, seg_start, seg_off, warp_tot};
+  const ScanSmem sm{stage64, stage32, stage_val, seg_start, seg_off, warp_tot};
 
   const int t = threadIdx.x;
   const int k = p.k;
@@ -99,7 +121,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     const bool last = R >= tg.rmax;
     if (last) R = tg.rmax;
     rg = make_region(g, tg, R);
-    scan_shell<T, true, false>(g, tg, rg, prev, have_prev, sm, cx, cy, cz, [&](int m) {
+    scan_shell<T, kStageCap, true, false, 0, false>(g, tg, rg, prev, have_prev, sm, cx, cy, cz, [&](int m) {
       if (active) {
 #pragma unroll 4
         for (int j = 0; j < m; ++j) {
@@ -169,40 +191,55 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   double wsum = 0.0, su = 0.0, sv = 0.0, sw = 0.0;  // idw accumulators
   double dsum = 0.0, ksum = 0.0;                    // sibson moments: sum d, sum d^2
   auto idw_weight = [&](double d2) { return 1.0 / ((p2 ? d2 : pow(sqrt(d2), p.power)) + eps); };
-  scan_shell<T, true, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
+  // float32 pre-test of one 64-candidate half chunk -> bit mask of the candidates that need the
+  // exact float64 key (the staged chunk is padded with far-away sentinels)
+  auto prefilter64 = [&](int base, float lim) {
+    unsigned long long msk = 0ULL;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      const float4 c = stage32[base + j];
+      const float dx = qfx - c.x, dy = qfy - c.y, dz = qfz - c.z;
+      const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      msk |= (unsigned long long)(d2f <= lim ? 1 : 0) << j;
+    }
+    return msk;
+  };
+  auto exact_d2 = [&](int j) {
+    const double2 xy = *reinterpret_cast<const double2*>(&stage64[j].x);
+    const double zz = stage64[j].z;
+    const double ex = qx - xy.x, ey = qy - xy.y, ez = qz - zz;
+    return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+  };
+  scan_shell<T, kExactCap, true, true, kVal, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
     if (active) {
-#pragma unroll 2
-      for (int j = 0; j < m; ++j) {
-        const float4 c = stage32[j];
-        const float dx = qfx - c.x, dy = qfy - c.y, dz = qfz - c.z;
-        const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d2f <= hi32) {
-          const double2 xy = *reinterpret_cast<const double2*>(&stage64[j].x);
-          const double zz = stage64[j].z;
-          const int pidx = stage64[j].idx;
-          const double ex = qx - xy.x, ey = qy - xy.y, ez = qz - zz;
-          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-          if (d2 < e_lo) {
-            ++n_in;
-            if (sib) {
-              dsum += sqrt(d2);
-              ksum += d2;
-            } else {
-              const double wgt = idw_weight(d2);
-              const Value4 val = g.vals[pidx];
-              wsum += wgt;
-              su += wgt * val.u;
-              sv += wgt * val.v;
-              sw += wgt * val.w;
-            }
-          } else if (d2 < e_hi) {
-            if (n_l < kListCap) {
-              lkey[n_l * T] = d2;
-              lidx[n_l * T] = pidx;
-              ++n_l;
-            } else {
-              overflow = true;
-            }
+      unsigned long long m0 = prefilter64(0, hi32);
+      unsigned long long m1 = m > 64 ? prefilter64(64, hi32) : 0ULL;
+      // each thread walks only ITS accepted candidates (dense per lane instead of "any lane")
+      while ((m0 | m1) != 0ULL) {
+        int j;
+        if (m0 != 0ULL) { j = __ffsll((long long)m0) - 1; m0 &= m0 - 1ULL; }
+        else { j = 64 + __ffsll((long long)m1) - 1; m1 &= m1 - 1ULL; }
+        const double d2 = exact_d2(j);
+        if (d2 < e_lo) {
+          ++n_in;
+          if (sib) {
+            dsum += sqrt(d2);
+            ksum += d2;
+          } else {
+            const double wgt = idw_weight(d2);
+            const ValT val = stage_val[j];
+            wsum += wgt;
+            su += wgt * (double)StageVal<OutT>::u(val);
+            sv += wgt * (double)StageVal<OutT>::v(val);
+            sw += wgt * (double)StageVal<OutT>::w(val);
+          }
+        } else if (d2 < e_hi) {
+          if (n_l < kListCap) {
+            lkey[n_l * T] = d2;
+            lidx[n_l * T] = stage64[j].idx;
+            ++n_l;
+          } else {
+            overflow = true;
           }
         }
       }
@@ -251,31 +288,33 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     const double mean = dsum / k;
     const double var = fmax(ksum / k - mean * mean, 0.0);
     const double inv_s = 1.0 / (sqrt(var) + eps);
-    auto sib_acc = [&](double d2, int pidx) {
+    auto sib_acc = [&](double d2, double vu, double vv, double vw) {
       const double d = sqrt(d2);
       const double wgt = (1.0 / (d + eps)) * exp(-d * inv_s);
-      const Value4 val = g.vals[pidx];
       wsum += wgt;
-      su += wgt * val.u;
-      sv += wgt * val.v;
-      sw += wgt * val.w;
+      su += wgt * vu;
+      sv += wgt * vv;
+      sw += wgt * vw;
     };
     if (active)
-      for (int i = 0; i < need; ++i) sib_acc(lkey[i * T], lidx[i * T]);
+      for (int i = 0; i < need; ++i) {
+        const Value4 val = g.vals[lidx[i * T]];
+        sib_acc(lkey[i * T], val.u, val.v, val.w);
+      }
     const float lo32 = (float)((e_lo + 16.0 * sqrt(e_lo) * ec + 64.0 * ec * ec) * (1.0 + 1e-5));
-    scan_shell<T, true, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
+    scan_shell<T, kExactCap, true, true, kVal, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
       if (active) {
-#pragma unroll 2
-        for (int j = 0; j < m; ++j) {
-          const float4 c = stage32[j];
-          const float dx = qfx - c.x, dy = qfy - c.y, dz = qfz - c.z;
-          const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          if (d2f <= lo32) {
-            const double2 xy = *reinterpret_cast<const double2*>(&stage64[j].x);
-            const double zz = stage64[j].z;
-            const double ex = qx - xy.x, ey = qy - xy.y, ez = qz - zz;
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-            if (d2 < e_lo) sib_acc(d2, stage64[j].idx);
+        unsigned long long m0 = prefilter64(0, lo32);
+        unsigned long long m1 = m > 64 ? prefilter64(64, lo32) : 0ULL;
+        while ((m0 | m1) != 0ULL) {
+          int j;
+          if (m0 != 0ULL) { j = __ffsll((long long)m0) - 1; m0 &= m0 - 1ULL; }
+          else { j = 64 + __ffsll((long long)m1) - 1; m1 &= m1 - 1ULL; }
+          const double d2 = exact_d2(j);
+          if (d2 < e_lo) {
+            const ValT val = stage_val[j];
+            sib_acc(d2, (double)StageVal<OutT>::u(val), (double)StageVal<OutT>::v(val),
+                    (double)StageVal<OutT>::w(val));
           }
         }
       }
@@ -297,9 +336,10 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   store_out<OutT>(p.w, vox, ow);
 }
 
-static size_t stream_smem_bytes(int T) {
+static size_t stream_smem_bytes(int T, bool f32) {
   const int NW = T / 32;
-  size_t b = (size_t)kListCap * T * 12 + (size_t)kStageCap * (sizeof(ParticleRec) + sizeof(float4)) +
+  size_t b = (size_t)kListCap * T * 12 +
+             (size_t)kStageCap * (sizeof(ParticleRec) + sizeof(float4) + (f32 ? sizeof(float4) : sizeof(Value4))) +
              (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 1 + NW) * sizeof(int);
   return (b + 15) & ~(size_t)15;
 }
@@ -311,7 +351,7 @@ static int launch_stream_t(KnnParams& p, cudaStream_t stream) {
   p.tiles_z = (p.nz + TZ - 1) / TZ;
   const int64_t ntiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
   if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
-  const size_t smem = stream_smem_bytes(T);
+  const size_t smem = stream_smem_bytes(T, sizeof(OutT) == 4);
   auto kern = knn_stream_kernel<T, TX, TY, TZ, OutT>;
   PTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)ntiles, T, smem, stream>>>(p);

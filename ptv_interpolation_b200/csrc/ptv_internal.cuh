@@ -24,7 +24,9 @@ struct __align__(16) Value4 {  // (u,v,w,0) in ORIGINAL particle order
 struct HashGrid {  // plain-old-data view passed to kernels by value
   const ParticleRec* rec;
   const int32_t* cell_start;  // [ncells+1], cell id = (cz*cny + cy)*cnx + cx
-  const Value4* vals;
+  const Value4* vals;         // (u,v,w,0) float64 in ORIGINAL particle order
+  const Value4* vals_s64;     // the same in cell-sorted order (parallel to rec)
+  const float4* vals_s32;     // float32 copy in cell-sorted order
   const double* pts;          // original (n,3) float64 rows (caller-owned; valid during the call that set it)
   double ox, oy, oz;          // origin = particle bbox minimum
   double cell, inv_cell;
@@ -58,6 +60,8 @@ struct ptv_hash {
   // device buffers (grown on demand, reused across builds)
   ptv::ParticleRec* rec = nullptr;
   ptv::Value4* vals = nullptr;
+  ptv::Value4* vals_s64 = nullptr;
+  float4* vals_s32 = nullptr;
   int32_t* cid = nullptr;
   int32_t* sorted_idx = nullptr;
   int32_t* cell_start = nullptr;  // ncells+1
