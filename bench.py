@@ -261,9 +261,8 @@ def run_b200(args):
         if record:
             e[2].record()
         w_below, w_above, m_above = comm.exchange_halos(uvw[2], mask_slab)
-        div, stats = eng.divergence(uvw[0], uvw[1], uvw[2], mask_slab, 1.0, 1.0, 1.0, w_below=w_below,
-                                    w_above=w_above, mask_above=m_above, with_stats=True)
-        q_xy, q_xz, q_yz = eng.flux_profiles(uvw[0], uvw[1], uvw[2])
+        div, stats, q_xy, q_xz, q_yz = eng.divergence_flux(uvw[0], uvw[1], uvw[2], mask_slab, 1.0, 1.0, 1.0,
+                                                           w_below=w_below, w_above=w_above, mask_above=m_above)
         comm.reduce_sum_(q_xz, q_yz, stats)
         q_xy = comm.gather_planes(q_xy)
         if record:
@@ -320,8 +319,8 @@ def run_b200(args):
             uvw = eng.interpolate(dax, dax, dax[z0:z1], mask=dm, method=method, k=k, out=out)
             hout.copy_(uvw, non_blocking=True)
             w_below, w_above, m_above = comm.exchange_halos(uvw[2], dm)
-            div, st = eng.divergence(uvw[0], uvw[1], uvw[2], dm, 1.0, 1.0, 1.0, w_below=w_below, w_above=w_above,
-                                     mask_above=m_above, with_stats=True)
+            div, st, _, _, _ = eng.divergence_flux(uvw[0], uvw[1], uvw[2], dm, 1.0, 1.0, 1.0, w_below=w_below,
+                                                   w_above=w_above, mask_above=m_above)
             comm.reduce_sum_(st)
             hstats.copy_(st, non_blocking=True)
 
@@ -361,8 +360,8 @@ def run_b200(args):
                 "note": "kNN selection is SM-issue bound, not HBM bound (DESIGN.md); the HBM-bound kernels are "
                         "listed under roofline_other"}
     st_ms = float(np.mean(phase_ms["stencils"]))
-    st_bytes = (17.0 + 12.0) * nzl * n * n  # divergence 17 B/vox + three 4 B/vox flux passes
-    roofline_other = [{"kernel": "divergence+flux (4 launches + halo/reduce)", "bound": "hbm",
+    st_bytes = 17.0 * nzl * n * n  # fused divergence + flux + statistics: 12 B u,v,w + 1 B mask read, 4 B div written
+    roofline_other = [{"kernel": "div_flux_kernel (1 launch + halo/reduce)", "bound": "hbm",
                        "achieved": st_bytes / (st_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": st_bytes / (st_ms * 1e-3) / 1e9 / peak, "ms": st_ms},
                       {"kernel": "hash build (10 launches)", "bound": "hbm",

@@ -128,6 +128,14 @@ int ptv_divergence(const void* d_u, const void* d_v, const void* d_w, const uint
 int ptv_flux_profiles(const void* d_u, const void* d_v, const void* d_w, int nx, int ny, int nz,
                       int dtype, double* d_qxy, double* d_qxz, double* d_qyz, void* stream);
 
+/* ---- the two above in ONE pass over the fields (what the pipeline uses): divergence, sum|div| and
+ *      fluid count, and the three unscaled flux profiles.  d_qxy/d_qxz/d_qyz: all three or all
+ *      NULL; they and d_absdiv_sum are accumulated into (zero them first). -------------------- */
+int ptv_divergence_flux(const void* d_u, const void* d_v, const void* d_w, const uint8_t* d_mask, int nx,
+                        int ny, int nz, double dx, double dy, double dz, const void* d_w_below,
+                        const void* d_w_above, const uint8_t* d_mask_above, int dtype, void* d_div,
+                        double* d_absdiv_sum, double* d_qxy, double* d_qxz, double* d_qyz, void* stream);
+
 /* ---- host-buffer convenience (what a non-CUDA caller binds): copies in, runs
  *      ptv_hash_build + ptv_knn_interp, copies out.  All pointers are HOST pointers. ------ */
 int ptv_interpolate_host(const double* h_points, const double* h_values, int64_t n,

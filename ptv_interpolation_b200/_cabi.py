@@ -22,7 +22,7 @@ _lib = None
 EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
     "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats",
-    "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence",
+    "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_interpolate_host",
 ]
 
@@ -66,6 +66,9 @@ def _declare(lib):
     lib.ptv_apply_mask.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     lib.ptv_divergence.restype = i32
     lib.ptv_divergence.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, vp, vp, vp, i32, vp, vp, vp]
+    lib.ptv_divergence_flux.restype = i32
+    lib.ptv_divergence_flux.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, vp, vp, vp, i32, vp, vp, vp, vp, vp,
+                                        vp]
     lib.ptv_flux_profiles.restype = i32
     lib.ptv_flux_profiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.ptv_interpolate_host.restype = i32

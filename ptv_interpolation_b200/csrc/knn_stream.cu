@@ -190,7 +190,13 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   const bool p2 = p.power == 2.0;
   double wsum = 0.0, su = 0.0, sv = 0.0, sw = 0.0;  // idw accumulators
   double dsum = 0.0, ksum = 0.0;                    // sibson moments: sum d, sum d^2
-  auto idw_weight = [&](double d2) { return 1.0 / ((p2 ? d2 : pow(sqrt(d2), p.power)) + eps); };
+  // float32 output: the weight only needs float32 accuracy (relative 6e-8, far inside the 1e-5 bar),
+  // so the reciprocal runs on the SFU; float64 output keeps the IEEE division.
+  auto idw_weight = [&](double d2) -> double {
+    const double den = (p2 ? d2 : pow(sqrt(d2), p.power)) + eps;
+    if (sizeof(OutT) == 4 && p2) return (double)__frcp_rn((float)den);  // den in [1e-10, ~1e12]: float32-safe
+    return 1.0 / den;
+  };
   // float32 pre-test of one 64-candidate half chunk -> bit mask of the candidates that need the
   // exact float64 key (the staged chunk is padded with far-away sentinels)
   auto prefilter64 = [&](int base, float lim) {

@@ -189,6 +189,24 @@ class PTVEngine:
                                                 self._stream()))
         return (div, stats) if with_stats else div
 
+    def divergence_flux(self, u, v, w, mask, dx, dy, dz, w_below=None, w_above=None, mask_above=None):
+        """One pass: (div, stats[2] = (sum|div| over fluid, n_fluid), q_xy[nz], q_xz[ny], q_yz[nx])."""
+        nz, ny, nx = u.shape
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        if mask_above is not None and mask_above.dtype == torch.bool:
+            mask_above = mask_above.view(torch.uint8)
+        u, v, w, mask = u.contiguous(), v.contiguous(), w.contiguous(), mask.contiguous()
+        div = torch.empty_like(u)
+        acc = torch.zeros(2 + nz + ny + nx, dtype=torch.float64, device=self.device)
+        stats, qxy, qxz, qyz = acc[:2], acc[2:2 + nz], acc[2 + nz:2 + nz + ny], acc[2 + nz + ny:]
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_divergence_flux(_ptr(u), _ptr(v), _ptr(w), _ptr(mask), nx, ny, nz, float(dx),
+                                                     float(dy), float(dz), _ptr(w_below), _ptr(w_above),
+                                                     _ptr(mask_above), _dtype_code(u.dtype), _ptr(div), _ptr(stats),
+                                                     _ptr(qxy), _ptr(qxz), _ptr(qyz), self._stream()))
+        return div, stats, qxy, qxz, qyz
+
     def flux_profiles(self, u, v, w):
         """Unscaled plane sums (q_xy[nz], q_xz[ny], q_yz[nx]) as float64 CUDA tensors."""
         ref = next(t for t in (u, v, w) if t is not None)

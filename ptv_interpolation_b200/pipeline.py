@@ -34,9 +34,8 @@ def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, c
                           out_dtype=out_dtype, out=out)
     w_below, w_above, m_above = comm.exchange_halos(uvw[2], mask_slab)
     dx, dy, dz = spacing
-    div, stats = eng.divergence(uvw[0], uvw[1], uvw[2], mask_slab, dx, dy, dz, w_below=w_below, w_above=w_above,
-                                mask_above=m_above, with_stats=True)
-    q_xy, q_xz, q_yz = eng.flux_profiles(uvw[0], uvw[1], uvw[2])
+    div, stats, q_xy, q_xz, q_yz = eng.divergence_flux(uvw[0], uvw[1], uvw[2], mask_slab, dx, dy, dz, w_below=w_below,
+                                                       w_above=w_above, mask_above=m_above)
     comm.reduce_sum_(q_xz, q_yz, stats)
     q_xy = comm.gather_planes(q_xy)
     return StepResult(uvw, div, q_xy, q_xz, q_yz, stats[0] / stats[1], stats[1])

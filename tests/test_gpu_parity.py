@@ -131,6 +131,33 @@ def test_divergence_flux_golden(golden_dir):
     assert d32.dtype == np.float32 and np.array_equal(d32, ref.astype(np.float32))
 
 
+@pytest.mark.parametrize("shape", [(11, 9, 7), (6, 10, 16), (5, 33, 1028), (3, 4, 2052)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_divergence_flux(shape, dtype):
+    rng = np.random.default_rng(shape[2])
+    u, v, w = (rng.normal(size=shape).astype(dtype) for _ in range(3))
+    m = rng.random(shape) > 0.35
+    h = (1.25, 0.75, 2.0) if shape[0] > 5 else (1.0, 1.0, 1.0)
+    eng = PTVEngine()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    div, st, qxy, qxz, qyz = eng.divergence_flux(t(u), t(v), t(w), t(m), *h)
+    u64, v64, w64 = (a.astype(np.float64) for a in (u, v, w))
+    ref = rp.compute_consistent_divergence(u64, v64, w64, m, *h)
+    assert np.array_equal(div.cpu().numpy(), ref.astype(dtype))
+    s, c = st.cpu().numpy()
+    assert c == m.sum()
+    assert abs(s / c - np.mean(np.abs(ref.astype(dtype).astype(np.float64)[m]))) <= 1e-12
+    assert np.allclose(qxy.cpu().numpy(), w64.sum(axis=(1, 2)), rtol=1e-12, atol=1e-10)
+    assert np.allclose(qxz.cpu().numpy(), v64.sum(axis=(0, 2)), rtol=1e-12, atol=1e-10)
+    assert np.allclose(qyz.cpu().numpy(), u64.sum(axis=(0, 1)), rtol=1e-12, atol=1e-10)
+    # slab form with halos reproduces the whole-grid result
+    if shape[0] >= 5:
+        a, b = 2, 4
+        d2, st2, *_ = eng.divergence_flux(t(u[a:b]), t(v[a:b]), t(w[a:b]), t(m[a:b]), *h, w_below=t(w[a - 1]),
+                                          w_above=t(w[b]), mask_above=t(m[b]).view(torch.uint8))
+        assert np.array_equal(d2.cpu().numpy(), ref[a:b].astype(dtype))
+
+
 def test_divergence_slab_halos_match_whole():
     rng = np.random.default_rng(9)
     shape = (12, 10, 9)
