@@ -316,13 +316,14 @@ def run_b200(args):
             dm.copy_(hm, non_blocking=True)
             dax.copy_(hax, non_blocking=True)
             eng.build(dp, dv)
-            uvw = eng.interpolate(dax, dax, dax[z0:z1], mask=dm, method=method, k=k, out=out)
-            hout.copy_(uvw, non_blocking=True)
+            # z-chunked search with the device->host copy of finished chunks overlapped on a second stream
+            uvw = eng.interpolate_to_host(dax, dax, dax[z0:z1], hout, mask=dm, dev_out=out, method=method, k=k)
             w_below, w_above, m_above = comm.exchange_halos(uvw[2], dm)
             div, st, _, _, _ = eng.divergence_flux(uvw[0], uvw[1], uvw[2], dm, 1.0, 1.0, 1.0, w_below=w_below,
                                                    w_above=w_above, mask_above=m_above)
             comm.reduce_sum_(st)
             hstats.copy_(st, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(eng.copy_stream)  # the step ends when U,V,W are on the host
 
         e2e_step()
         barrier()

@@ -110,8 +110,8 @@ class PTVEngine:
             mask = mask.contiguous()
         if out is None:
             out = torch.empty((3, nz, ny, nx), dtype=out_dtype, device=self.device)
-        elif tuple(out.shape) != (3, nz, ny, nx) or not out.is_contiguous():
-            raise ValueError("out must be a contiguous (3, nz, ny, nx) tensor")
+        elif tuple(out.shape) != (3, nz, ny, nx) or not out[0].is_contiguous():
+            raise ValueError("out must be a (3, nz, ny, nx) tensor whose components are contiguous")
         if method == "nearest":
             k = 1
         kd = ki = None
@@ -126,6 +126,36 @@ class PTVEngine:
         if return_knn:
             return out, kd, ki
         return out
+
+    def interpolate_to_host(self, ax_x, ax_y, ax_z, host_out, mask=None, dev_out=None, chunks=None, **kw):
+        """interpolate() with the device->host copy of U,V,W overlapped with the search: the slab is
+        processed in z-chunks on the current stream while a second stream drains finished chunks into
+        ``host_out`` (a pinned (3,nz,ny,nx) CPU tensor).  Returns the device tensor; the caller must
+        synchronise (``torch.cuda.synchronize()`` or ``self.copy_stream.synchronize()``) before reading
+        ``host_out``."""
+        nx, ny, nz = ax_x.numel(), ax_y.numel(), ax_z.numel()
+        if dev_out is None:
+            dev_out = torch.empty((3, nz, ny, nx), dtype=host_out.dtype, device=self.device)
+        if tuple(host_out.shape) != (3, nz, ny, nx) or host_out.dtype != dev_out.dtype:
+            raise ValueError("host_out must be a (3, nz, ny, nx) CPU tensor of the output dtype")
+        if chunks is None:
+            chunks = max(1, min(16, nz // 16))
+        if not hasattr(self, "copy_stream"):
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        cuts = [round(i * nz / chunks) for i in range(chunks + 1)]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b <= a:
+                continue
+            self.interpolate(ax_x, ax_y, ax_z[a:b], mask=None if mask is None else mask[a:b],
+                             out=dev_out[:, a:b], **kw)
+            done = torch.cuda.Event()
+            done.record(main)
+            self.copy_stream.wait_event(done)
+            with torch.cuda.stream(self.copy_stream):
+                for c in range(3):
+                    host_out[c, a:b].copy_(dev_out[c, a:b], non_blocking=True)
+        return dev_out
 
     def knn_stats(self):
         """Diagnostics of the last interpolate(): did the streaming kernel run, how many tiles fell

@@ -121,17 +121,17 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     if mask is not None:
         m = torch.from_numpy(np.ascontiguousarray(mask).astype(np.uint8, copy=False)).to(dev)
     tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
-    res = eng.interpolate(ax[0], ax[1], ax[2], mask=m, method=method, k=int(k), idw_power=float(idw_power),
-                          smoothing=float(smoothing), out_dtype=tdt, return_knn=return_knn)
+    kw = dict(method=method, k=int(k), idw_power=float(idw_power), smoothing=float(smoothing))
     if return_knn:
-        out, kd, ki = res
-    else:
-        out = res
-    host = out.cpu().numpy()
-    U, V, W = host[0], host[1], host[2]
-    if return_knn:
-        return U, V, W, kd.cpu().numpy(), ki.cpu().numpy()
-    return U, V, W
+        out, kd, ki = eng.interpolate(ax[0], ax[1], ax[2], mask=m, out_dtype=tdt, return_knn=True, **kw)
+        host = out.cpu().numpy()
+        return host[0], host[1], host[2], kd.cpu().numpy(), ki.cpu().numpy()
+    # pinned result buffer, filled chunk by chunk while later z-chunks are still being searched
+    host_t = torch.empty((3, len(z), len(y), len(x)), dtype=tdt, pin_memory=True)
+    eng.interpolate_to_host(ax[0], ax[1], ax[2], host_t, mask=m, **kw)
+    torch.cuda.synchronize(dev)
+    host = host_t.numpy()
+    return host[0], host[1], host[2]
 
 
 def _nearest_axis_index(src_coords, q):
