@@ -92,6 +92,10 @@ int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, const double
  * how many voxel tiles it handed to the exact heap kernel, and (with tuning "stats" = 1) how many it
  * finished itself.  Synchronises the device. */
 int ptv_knn_stats(const ptv_hash* h, int64_t* used_stream, int64_t* tiles_failed, int64_t* tiles_streamed);
+/* With tuning "stats" = 1: why tiles were handed over -- [0] no local density estimate, [1] k-th
+ * neighbour beyond the histogram range, [2] crossing bin larger than the short list, [3] exact
+ * verification failed. */
+int ptv_knn_fail_reasons(const ptv_hash* h, int64_t reasons[4]);
 
 /* ---- mask resampling: replaces sample_mask_on_grid (interpolator.py:205-238).  The
  *      per-axis nearest index maps (-1 == out of bounds) are computed by the host shim with

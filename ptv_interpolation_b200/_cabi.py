@@ -21,7 +21,7 @@ _lib = None
 
 EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
-    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats",
+    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons",
     "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_interpolate_host",
 ]
@@ -58,6 +58,8 @@ def _declare(lib):
     lib.ptv_knn_interp.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp, vp]
     lib.ptv_knn_stats.restype = i32
     lib.ptv_knn_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    lib.ptv_knn_fail_reasons.restype = i32
+    lib.ptv_knn_fail_reasons.argtypes = [vp, C.POINTER(i64 * 4)]
     lib.ptv_mask_gather.restype = i32
     lib.ptv_mask_gather.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
     lib.ptv_boundary_voxels.restype = i32

@@ -14,7 +14,7 @@ static int ensure_fail_buffers(ptv_hash* h, int64_t ntiles) {
     PTV_CUDA(cudaMalloc(&h->fail_list, (size_t)(ntiles + 1024) * sizeof(int)));
     h->fail_cap = ntiles + 1024;
   }
-  if (h->fail_count == nullptr) PTV_CUDA(cudaMalloc(&h->fail_count, 4 * sizeof(unsigned long long)));
+  if (h->fail_count == nullptr) PTV_CUDA(cudaMalloc(&h->fail_count, 8 * sizeof(unsigned long long)));
   return PTV_OK;
 }
 
@@ -95,7 +95,7 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
     if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
     rc = ensure_fail_buffers(h, ntiles);
     if (rc != PTV_OK) return rc;
-    PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, 4 * sizeof(unsigned long long), stream));
+    PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, 8 * sizeof(unsigned long long), stream));
     p.fail_list = h->fail_list;
     p.fail_count = reinterpret_cast<int*>(h->fail_count);
     p.stats = tuning().stats != 0 ? h->fail_count + 1 : nullptr;
@@ -115,6 +115,15 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
     PTV_CUDA(cudaStreamSynchronize(stream));
     if (*h->err_host != 0) { set_error("Singular matrix."); return PTV_ERR_SINGULAR; }
   }
+  return PTV_OK;
+}
+
+extern "C" int ptv_knn_fail_reasons(const ptv_hash* h, int64_t reasons[4]) {
+  if (!h || !reasons) { set_error("ptv_knn_fail_reasons: NULL argument"); return PTV_ERR_INVALID; }
+  unsigned long long host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (h->last_used_stream && h->fail_count != nullptr)
+    PTV_CUDA(cudaMemcpy(host, h->fail_count, sizeof(host), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) reasons[i] = (int64_t)host[2 + i];
   return PTV_OK;
 }
 

@@ -23,7 +23,7 @@
 
 namespace ptv {
 
-static constexpr int kNB = 32;        // histogram bins over [0, Tmax)
+static constexpr int kNB = 48;        // histogram bins over [0, Tmax)
 static constexpr int kListCap = 20;   // capacity of the crossing-bin list
 static constexpr int kMinEstimate = 16;
 static constexpr int kExactCap = 128;  // chunk size of the exact passes (two 64-bit accept masks)
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   double* lkey_all = reinterpret_cast<double*>(smem_raw);                       // [kListCap][T]
   int* lidx_all = reinterpret_cast<int*>(lkey_all + (size_t)kListCap * T);      // [kListCap][T]
   int* hist_all = reinterpret_cast<int*>(smem_raw);                             // [kNB][T] (alias)
-  static_assert(kNB * 4 <= kListCap * 8, "histogram must fit under the list keys");
+  static_assert(kNB * 4 <= kListCap * 12, "histogram must fit under the list");
   ParticleRec* stage64 = reinterpret_cast<ParticleRec*>(lidx_all + (size_t)kListCap * T);
   float4* stage32 = reinterpret_cast<float4*>(stage64 + kStageCap);
   using ValT = typename StageVal<OutT>::type;  // float4 for float32 output, Value4 for float64 output
@@ -101,13 +101,16 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   // ---- local density -> radius schedule and histogram scale
   const double r_est = estimate_radius<T>(g, tg, p.r0, k, kMinEstimate, warp_tot);
   if (!(r_est > 0.0)) {  // nothing to estimate a scale from (deep void / tiny cloud): exact kernel
-    if (t == 0) p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+    if (t == 0) {
+      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+      if (p.stats != nullptr) atomicAdd(&p.stats[1], 1ULL);  // fail reason 1
+    }
     return;
   }
-  // three scan radii whose squares sit just above histogram bin edges 12, 20 and 32 (= Tmax)
-  const double binw = 1.3 * r_est * r_est / 12.0;
+  // three scan radii whose squares sit just above histogram bin edges 18, 30 and 48 (= Tmax)
+  const double binw = 1.3 * r_est * r_est / 18.0;
   const float inv_w = (float)(1.0 / binw);
-  constexpr int kEdges[3] = {12, 20, kNB};
+  constexpr int kEdges[3] = {18, 30, kNB};
 
   // ---- phase A: grow the scanned region, float32 histogram of squared distances
   int* hist = hist_all + t;
@@ -147,7 +150,10 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     have_prev = true;
   }
   if (!finished) {  // the k-th neighbour is beyond the histogram range for some voxel
-    if (t == 0) p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+    if (t == 0) {
+      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+      if (p.stats != nullptr) atomicAdd(&p.stats[2], 1ULL);  // fail reason 2
+    }
     return;
   }
 
@@ -172,7 +178,10 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     if (rg.R < tg.rmax && e_hi > (rg.R - 1e-6 * g.cell) * (rg.R - 1e-6 * g.cell)) fail = true;
   }
   if (__syncthreads_or(fail ? 1 : 0)) {
-    if (t == 0) p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+    if (t == 0) {
+      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+      if (p.stats != nullptr) atomicAdd(&p.stats[3], 1ULL);  // fail reason 3
+    }
     return;
   }
 
@@ -254,7 +263,10 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   const int need = k - n_in;
   const bool bad = active && (overflow || need < 0 || need > n_l);
   if (__syncthreads_or(bad ? 1 : 0)) {
-    if (t == 0) p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+    if (t == 0) {
+      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
+      if (p.stats != nullptr) atomicAdd(&p.stats[4], 1ULL);  // fail reason 4
+    }
     return;
   }
 

@@ -162,7 +162,10 @@ class PTVEngine:
         back to the exact heap kernel, how many it finished itself (needs set_tuning(stats=1))."""
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _cabi.check(self.lib.ptv_knn_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"used_stream": bool(a.value), "tiles_failed": b.value, "tiles_streamed": c.value}
+        r = (C.c_int64 * 4)()
+        _cabi.check(self.lib.ptv_knn_fail_reasons(self._h, C.byref(r)))
+        return {"used_stream": bool(a.value), "tiles_failed": b.value, "tiles_streamed": c.value,
+                "fail_reasons": {"no_estimate": r[0], "beyond_range": r[1], "bin_overflow": r[2], "verify": r[3]}}
 
     # ------------------------------------------------------------------ grid ops
     def mask_gather(self, mask_raw, ix, iy, iz):
