@@ -355,7 +355,9 @@ def run_b200(args):
     knn_ms = float(np.mean(phase_ms["interp"]))
     algo_bytes = ALGO_BYTES_PER_VOXEL * nzl * n * n + ALGO_BYTES_PER_PARTICLE * npart
     achieved = algo_bytes / (knn_ms * 1e-3) / 1e9
-    roofline = {"kernel": "knn_interp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    used_stream = eng.knn_stats()["used_stream"]
+    roofline = {"kernel": "knn_stream_kernel (+ knn_interp_kernel on handed-over tiles)" if used_stream
+                else "knn_interp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": knn_ms,
                 "note": "kNN selection is SM-issue bound, not HBM bound (DESIGN.md); the HBM-bound kernels are "

@@ -403,3 +403,82 @@ def test_rbf_sphere_pack_vs_oracle_and_errors():
         gi.interpolate_field(_df(flat, vals[:300]), grid, method="rbf")
     with pytest.raises(ValueError):  # fewer than 4 points: RBFInterpolator raises ValueError
         gi.interpolate_field(_df(pts[:3], vals[:3]), grid, method="rbf")
+
+
+# ------------------------------------------------------------------ BASELINE-size checks (c2 / c3 geometry)
+def _full_size_case(name, device):
+    cfg = synthetic.make_config(name, device=device)
+    n = cfg["n"]
+    ax = torch.linspace(0, n - 1, n, dtype=torch.float64, device=device)
+    return cfg, n, ax
+
+
+def test_c2_full_size_planes_vs_oracle_and_properties():
+    """Config 2 (256^3, 1M vectors, IDW k=50): three whole z-planes against the oracle (cKDTree over all
+    1M particles), plus size-independent properties on the whole grid: constant field -> constant, solid
+    voxels exactly zero, slab-by-slab launch == whole-grid launch, divergence/flux consistency."""
+    dev = torch.device("cuda", 0)
+    cfg, n, ax = _full_size_case("c2", dev)
+    eng = PTVEngine(dev)
+    mask = cfg["mask"].view(torch.uint8)
+    eng.build(cfg["points"], cfg["values"])
+    out = eng.interpolate(ax, ax, ax, mask=mask, method="idw", k=50, out_dtype=torch.float64)
+    pts, vals = cfg["points"].cpu().numpy(), cfg["values"].cpu().numpy()
+    mask_np = cfg["mask"].cpu().numpy()
+    assert torch.all(out[:, ~cfg["mask"]] == 0)
+    from scipy.spatial import KDTree
+    tree = KDTree(pts)
+    axn = np.linspace(0, n - 1, n)
+    for z in (0, 97, 255):
+        Z, Y, X = np.meshgrid(axn[z:z + 1], axn, axn, indexing="ij")
+        fc = np.stack([X.ravel(), Y.ravel(), Z.ravel()], -1)
+        d, i, _ = rp.knn_canonical(pts, fc, 50, workers=-1, tree=tree)
+        ref = np.moveaxis(rp.idw_from_knn(d, i, vals).reshape(1, n, n, 3), -1, 0)
+        ref = ref * mask_np[z][None, None]
+        _assert_vel(out[:, z:z + 1].cpu().numpy(), ref, vals)
+    # slab-by-slab == whole grid (what the z-slab sharding relies on)
+    part = eng.interpolate(ax, ax, ax[100:140], mask=mask[100:140], method="idw", k=50, out_dtype=torch.float64)
+    assert torch.allclose(part, out[:, 100:140], rtol=0, atol=1e-11)
+    # constant field -> constant in the pore space
+    eng.build(cfg["points"], torch.full_like(cfg["values"], 3.25))
+    const = eng.interpolate(ax, ax, ax, mask=mask, method="idw", k=50)
+    pore = const[:, cfg["mask"]]
+    assert float((pore - 3.25).abs().max()) <= 1e-5
+    # divergence + flux of the float32 field: slab halves with halos == whole grid
+    f32 = out.to(torch.float32)
+    div, st, qxy, qxz, qyz = eng.divergence_flux(f32[0], f32[1], f32[2], mask, 1.0, 1.0, 1.0)
+    h = n // 2
+    d0, s0, a0, b0, c0 = eng.divergence_flux(f32[0, :h], f32[1, :h], f32[2, :h], mask[:h], 1.0, 1.0, 1.0,
+                                             w_above=f32[2, h].contiguous(), mask_above=mask[h].contiguous())
+    d1, s1, a1, b1, c1 = eng.divergence_flux(f32[0, h:], f32[1, h:], f32[2, h:], mask[h:], 1.0, 1.0, 1.0,
+                                             w_below=f32[2, h - 1].contiguous())
+    assert torch.equal(torch.cat([d0, d1]), div)
+    assert torch.allclose(s0 + s1, st, rtol=1e-12) and torch.allclose(torch.cat([a0, a1]), qxy, rtol=1e-12)
+    assert torch.allclose(b0 + b1, qxz, rtol=1e-11, atol=1e-9) and torch.allclose(c0 + c1, qyz, rtol=1e-11, atol=1e-9)
+    assert torch.allclose(qyz, f32[0].double().sum(dim=(0, 1)), rtol=1e-11, atol=1e-8)
+
+
+def test_c3_size_sibson_sampled_voxels_vs_oracle():
+    """Config 3 geometry (FCC pack, sibson k=50) at 512^3 / 5M vectors: 20k random pore voxels of the
+    full-grid result against the oracle, and checksum equality between two runs (determinism)."""
+    dev = torch.device("cuda", 0)
+    cfg, n, ax = _full_size_case("c3", dev)
+    eng = PTVEngine(dev)
+    mask = cfg["mask"].view(torch.uint8)
+    eng.build(cfg["points"], cfg["values"])
+    out = eng.interpolate(ax, ax, ax, mask=mask, method="sibson", k=50, out_dtype=torch.float64)
+    chk = out.sum(dtype=torch.float64)
+    out2 = eng.interpolate(ax, ax, ax, mask=mask, method="sibson", k=50, out_dtype=torch.float64)
+    assert torch.equal(out, out2) and chk == out2.sum(dtype=torch.float64)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    lin = torch.nonzero(cfg["mask"].reshape(-1)).squeeze(1)
+    sel = lin[torch.randint(0, lin.numel(), (20000,), generator=g, device=dev)]
+    zz, rem = sel // (n * n), sel % (n * n)
+    yy, xx = rem // n, rem % n
+    q = torch.stack([xx, yy, zz], -1).to(torch.float64).cpu().numpy()
+    pts, vals = cfg["points"].cpu().numpy(), cfg["values"].cpu().numpy()
+    d, i, _ = rp.knn_canonical(pts, q, 50, workers=-1)
+    ref = rp.sibson_from_knn(d, i, vals).T
+    got = out.reshape(3, -1)[:, sel].cpu().numpy()
+    _assert_vel(got[:, None, None, :], ref[:, None, None, :], vals)
