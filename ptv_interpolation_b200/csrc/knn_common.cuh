@@ -25,6 +25,7 @@ struct KnnParams {
   double* knn_dist;
   int tiles_x, tiles_y, tiles_z;
   int r0;
+  double rscale;  // stream kernel: first scan radius^2 = rscale * r_est^2
   double smoothing;
   int* err_flag;
   // stream kernel -> heap kernel hand-off: tiles the optimistic kernel could not finish

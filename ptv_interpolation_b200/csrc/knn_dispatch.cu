@@ -66,6 +66,7 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
   p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
   p.smoothing = rbf_smoothing;
+  p.rscale = tuning().rscale;
   p.err_flag = h->err_flag;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.tiles_x = p.tiles_y = p.tiles_z = 0;
@@ -118,12 +119,15 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   return PTV_OK;
 }
 
-extern "C" int ptv_knn_fail_reasons(const ptv_hash* h, int64_t reasons[4]) {
+extern "C" int ptv_knn_fail_reasons(const ptv_hash* hc, int64_t reasons[4]) {
+  ptv_hash* h = const_cast<ptv_hash*>(hc);
   if (!h || !reasons) { set_error("ptv_knn_fail_reasons: NULL argument"); return PTV_ERR_INVALID; }
   unsigned long long host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (h->last_used_stream && h->fail_count != nullptr)
     PTV_CUDA(cudaMemcpy(host, h->fail_count, sizeof(host), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) reasons[i] = (int64_t)host[2 + i];
+  h->last_stage_counts[0] = (int64_t)host[6];
+  h->last_stage_counts[1] = (int64_t)host[7];
   return PTV_OK;
 }
 

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     return;
   }
   // three scan radii whose squares sit just above histogram bin edges 18, 30 and 48 (= Tmax)
-  const double binw = 1.3 * r_est * r_est / 18.0;
+  const double binw = p.rscale * r_est * r_est / 18.0;
   const float inv_w = (float)(1.0 / binw);
   constexpr int kEdges[3] = {18, 30, kNB};
 
@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
       for (int b = 0; b < nfull; ++b) cum += hist[b * T];
       done = cum >= k;
     }
-    if (__syncthreads_and(done ? 1 : 0) || last) { finished = true; break; }
+    if (__syncthreads_and(done ? 1 : 0) || last) {
+      finished = true;
+      if (p.stats != nullptr && t == 0 && stage > 0) atomicAdd(&p.stats[4 + stage], 1ULL);  // finished at stage 1 / 2
+      break;
+    }
     prev = rg;
     have_prev = true;
   }

@@ -44,6 +44,7 @@ struct Tuning {
   int stream = 1;    // 1 = streaming kernel for idw/sibson with k >= 8 (heap kernel as fallback)
   int stream_tile = 128;
   int stats = 0;     // 1 = count streamed tiles
+  double rscale = 1.3;  // stream kernel: first scan radius^2 = rscale * r_est^2
 };
 Tuning& tuning();
 void count_launches(int n);
@@ -75,6 +76,7 @@ struct ptv_hash {
   int64_t fail_cap = 0;
   unsigned long long* fail_count = nullptr;  // [0] low 32 bits: fail count; [1]: streamed tiles (stats)
   bool last_used_stream = false;
+  int64_t last_stage_counts[2] = {0, 0};
   int64_t cap_n = 0;
   int64_t cap_cells = 0;
   int64_t cap_scan = 0;
