@@ -67,31 +67,80 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   int* warp_tot = seg_off + T + 1;
   const ScanSmem sm{stage64, stage32, stage_val, seg_start, seg_off, warp_tot};
 
+  uint16_t* vlist = reinterpret_cast<uint16_t*>(warp_tot + NW + 1);  // [4*T] compacted active voxels
+
   const int t = threadIdx.x;
   const int k = p.k;
   const HashGrid& g = p.g;
-  const int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x;
-  const int ty = (tile / p.tiles_x) % p.tiles_y;
-  const int tz = tile / (p.tiles_x * p.tiles_y);
-  const int ix = tx * TX + (t % TX);
-  const int iy = ty * TY + ((t / TX) % TY);
-  const int iz = tz * TZ + (t / (TX * TY));
-  const bool valid = ix < p.nx && iy < p.ny && iz < p.nz;
-  const int64_t vox = valid ? ((int64_t)iz * p.ny + iy) * p.nx + ix : 0;
-  const bool active = valid && (p.mask == nullptr || p.mask[vox] != 0);
-
-  if (!__syncthreads_or(active ? 1 : 0)) {  // tile entirely solid / outside: zero fill
-    if (valid) {
-      store_out<OutT>(p.u, vox, 0.0);
-      store_out<OutT>(p.v, vox, 0.0);
-      store_out<OutT>(p.w, vox, 0.0);
+  // ---- region of 4*T voxels (4x4x4 blocks, block-major) -> compact list of its ACTIVE voxels, so
+  //      that every lane of a round owns a pore voxel even where the tile straddles a grain surface
+  constexpr int RX = 8, RY = T >= 64 ? 8 : 4, RZ = T == 128 ? 8 : 4;
+  constexpr int NBX = RX / 4, NBY = RY / 4;
+  static_assert(RX * RY * RZ == 4 * T, "region holds four voxels per thread");
+  const int region = blockIdx.x;
+  const int rx = region % p.tiles_x;
+  const int ry = (region / p.tiles_x) % p.tiles_y;
+  const int rz = region / (p.tiles_x * p.tiles_y);
+  auto decode = [&](int i, int& ix, int& iy, int& iz) {
+    const int b = i >> 6, l = i & 63;
+    ix = rx * RX + (b % NBX) * 4 + (l & 3);
+    iy = ry * RY + ((b / NBX) % NBY) * 4 + ((l >> 2) & 3);
+    iz = rz * RZ + (b / (NBX * NBY)) * 4 + (l >> 4);
+  };
+  auto push_fail = [&](int reason) {  // hand every heap tile of this region to the exact kernel
+    if (t == 0) {
+      const int htx = (p.nx + TX - 1) / TX, hty = (p.ny + TY - 1) / TY, htz = (p.nz + TZ - 1) / TZ;
+      for (int cz2 = 0; cz2 < RZ / TZ; ++cz2)
+        for (int cy2 = 0; cy2 < RY / TY; ++cy2)
+          for (int cx2 = 0; cx2 < RX / TX; ++cx2) {
+            const int hx = rx * (RX / TX) + cx2, hy = ry * (RY / TY) + cy2, hz = rz * (RZ / TZ) + cz2;
+            if (hx < htx && hy < hty && hz < htz)
+              p.fail_list[atomicAdd(p.fail_count, 1)] = (hz * hty + hy) * htx + hx;
+          }
+      if (p.stats != nullptr) atomicAdd(&p.stats[reason], 1ULL);
     }
-    return;
+  };
+  int nact;
+  {
+    int mine = 0;
+    unsigned flags = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int ix, iy, iz;
+      decode(4 * t + q, ix, iy, iz);
+      if (ix < p.nx && iy < p.ny && iz < p.nz) {
+        const int64_t vox = ((int64_t)iz * p.ny + iy) * p.nx + ix;
+        if (p.mask == nullptr || p.mask[vox] != 0) {
+          flags |= 1u << q;
+          ++mine;
+        } else {  // solid voxel: main.py:202-207 writes zero
+          store_out<OutT>(p.u, vox, 0.0);
+          store_out<OutT>(p.v, vox, 0.0);
+          store_out<OutT>(p.w, vox, 0.0);
+        }
+      }
+    }
+    const int off = block_scan_excl<T>(mine, warp_tot, &nact);
+    int o = off;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (flags & (1u << q)) vlist[o++] = (uint16_t)(4 * t + q);
   }
-  const double qx = valid ? p.ax[ix] : 0.0;
-  const double qy = valid ? p.ay[iy] : 0.0;
-  const double qz = valid ? p.az[iz] : 0.0;
+  if (nact == 0) return;
+  __syncthreads();
+  const int rounds = (nact + T - 1) / T;
+  int round_start = 0;
+  for (int round = 0; round < rounds; ++round) {
+  const int round_cnt = nact / rounds + (round < nact % rounds ? 1 : 0);
+  const bool active = t < round_cnt;
+  const bool valid = active;
+  int ix = 0, iy = 0, iz = 0;
+  if (active) decode(vlist[round_start + t], ix, iy, iz);
+  round_start += round_cnt;
+  const int64_t vox = active ? ((int64_t)iz * p.ny + iy) * p.nx + ix : 0;
+  const double qx = active ? p.ax[ix] : 0.0;
+  const double qy = active ? p.ay[iy] : 0.0;
+  const double qz = active ? p.az[iz] : 0.0;
 
   TileGeom tg;
   tile_geometry<T>(g, active, qx, qy, qz, red, tg);
@@ -101,10 +150,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   // ---- local density -> radius schedule and histogram scale
   const double r_est = estimate_radius<T>(g, tg, p.r0, k, kMinEstimate, warp_tot);
   if (!(r_est > 0.0)) {  // nothing to estimate a scale from (deep void / tiny cloud): exact kernel
-    if (t == 0) {
-      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
-      if (p.stats != nullptr) atomicAdd(&p.stats[1], 1ULL);  // fail reason 1
-    }
+    push_fail(1);
     return;
   }
   // three scan radii whose squares sit just above histogram bin edges 18, 30 and 48 (= Tmax)
@@ -154,10 +200,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     have_prev = true;
   }
   if (!finished) {  // the k-th neighbour is beyond the histogram range for some voxel
-    if (t == 0) {
-      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
-      if (p.stats != nullptr) atomicAdd(&p.stats[2], 1ULL);  // fail reason 2
-    }
+    push_fail(2);
     return;
   }
 
@@ -182,10 +225,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     if (rg.R < tg.rmax && e_hi > (rg.R - 1e-6 * g.cell) * (rg.R - 1e-6 * g.cell)) fail = true;
   }
   if (__syncthreads_or(fail ? 1 : 0)) {
-    if (t == 0) {
-      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
-      if (p.stats != nullptr) atomicAdd(&p.stats[3], 1ULL);  // fail reason 3
-    }
+    push_fail(3);
     return;
   }
 
@@ -267,10 +307,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   const int need = k - n_in;
   const bool bad = active && (overflow || need < 0 || need > n_l);
   if (__syncthreads_or(bad ? 1 : 0)) {
-    if (t == 0) {
-      p.fail_list[atomicAdd(p.fail_count, 1)] = tile;
-      if (p.stats != nullptr) atomicAdd(&p.stats[4], 1ULL);  // fail reason 4
-    }
+    push_fail(4);
     return;
   }
 
@@ -344,33 +381,34 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   }
 
   if (p.stats != nullptr && t == 0) atomicAdd(&p.stats[0], 1ULL);
-  if (!valid) return;
-  double ou = 0.0, ov = 0.0, ow = 0.0;
   if (active) {
-    ou = su / wsum; ov = sv / wsum; ow = sw / wsum;
+    double ou = su / wsum, ov = sv / wsum, ow = sw / wsum;
     // main.py:195-199 nan_to_num
     if (ou != ou) ou = 0.0;
     if (ov != ov) ov = 0.0;
     if (ow != ow) ow = 0.0;
+    store_out<OutT>(p.u, vox, ou);
+    store_out<OutT>(p.v, vox, ov);
+    store_out<OutT>(p.w, vox, ow);
   }
-  store_out<OutT>(p.u, vox, ou);
-  store_out<OutT>(p.v, vox, ov);
-  store_out<OutT>(p.w, vox, ow);
+  __syncthreads();  // shared memory is reused by the next round
+  }  // rounds
 }
 
 static size_t stream_smem_bytes(int T, bool f32) {
   const int NW = T / 32;
   size_t b = (size_t)kListCap * T * 12 +
              (size_t)kStageCap * (sizeof(ParticleRec) + sizeof(float4) + (f32 ? sizeof(float4) : sizeof(Value4))) +
-             (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 1 + NW) * sizeof(int);
+             (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 2 + NW) * sizeof(int) + (size_t)4 * T * sizeof(uint16_t);
   return (b + 15) & ~(size_t)15;
 }
 
 template <int T, int TX, int TY, int TZ, typename OutT>
 static int launch_stream_t(KnnParams& p, cudaStream_t stream) {
-  p.tiles_x = (p.nx + TX - 1) / TX;
-  p.tiles_y = (p.ny + TY - 1) / TY;
-  p.tiles_z = (p.nz + TZ - 1) / TZ;
+  constexpr int RX = 8, RY = T >= 64 ? 8 : 4, RZ = T == 128 ? 8 : 4;  // region = four voxels per thread
+  p.tiles_x = (p.nx + RX - 1) / RX;
+  p.tiles_y = (p.ny + RY - 1) / RY;
+  p.tiles_z = (p.nz + RZ - 1) / RZ;
   const int64_t ntiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
   if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
   const size_t smem = stream_smem_bytes(T, sizeof(OutT) == 4);
