@@ -42,6 +42,7 @@ extern "C" {
 #define PTV_METHOD_SIBSON 1  /* interpolator.py:83-124  */
 #define PTV_METHOD_NEAREST 2 /* interpolator.py:197 griddata(method='nearest') == k=1 */
 #define PTV_METHOD_RBF 3     /* interpolator.py:157-195 local thin-plate-spline RBF */
+#define PTV_METHOD_MADFILTER 4 /* internal: filtering.py:5-58, reached through ptv_outlier_filter */
 
 /* output element types for the velocity grids */
 #define PTV_F32 0
@@ -87,6 +88,21 @@ int ptv_knn_interp(const ptv_hash* h, const double* d_ax_x, int nx, const double
                    const double* d_ax_z, int nz, const uint8_t* d_mask, int method, int k,
                    double idw_power, double rbf_smoothing, int out_dtype, void* d_u, void* d_v,
                    void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream);
+
+/* ---- the same search and weights for ARBITRARY query points (non-rectilinear grid_tuple, or the
+ *      particles themselves).  `queries` is a second hash built over the query points (its values are
+ *      ignored; pass h itself for a self-query): its cell order keeps tiles of 128 queries compact.
+ *      Outputs are indexed by the query's original row: d_u/d_v/d_w [nq] (nullable together),
+ *      d_knn_idx/d_knn_dist [nq][k] (nullable together). ------------------------------------------ */
+int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int method, int k, double idw_power,
+                   double rbf_smoothing, int out_dtype, void* d_u, void* d_v, void* d_w, int64_t* d_knn_idx,
+                   double* d_knn_dist, void* stream);
+
+/* ---- kNN median/MAD outlier filter: replaces remove_outliers_knn (filtering.py:5-58).  Self-query
+ *      with k+1 neighbours, first neighbour dropped, z = |speed - median| / (MAD + 1e-6);
+ *      d_keep[i] = z <= threshold, d_kth_dist[i] = distance to the k-th neighbour (filtering.py:33). */
+int ptv_outlier_filter(const ptv_hash* h, int k, double threshold, uint8_t* d_keep, double* d_kth_dist,
+                       void* stream);
 
 /* Diagnostics of the last ptv_knn_interp call on this handle: whether the streaming kernel ran,
  * how many voxel tiles it handed to the exact heap kernel, and (with tuning "stats" = 1) how many it

@@ -142,6 +142,22 @@ def main():
     ge, _ = ri.create_grid(((0, 10), (0, 10), (0, 10)), 10)
     U, V, W = ri.interpolate_field(dfe, ge, method="rbf", n_jobs=2)
     np.savez_compressed(os.path.join(OUT, "case_e_test_parallel.npz"), uvw=np.stack([U, V, W], 0))
+    # ---- case F: kNN median/MAD outlier filter (filtering.py:5-58), with planted outliers
+    sys.path.insert(0, REF)
+    import filtering as rf
+    sys.path.pop(0)
+    rng = np.random.default_rng(606)
+    pf_ = f32r(rng.uniform(0, 20, size=(3000, 3)))
+    vf_ = f32r(np.stack([1 + 0.1 * pf_[:, 1], 0.2 * np.sin(pf_[:, 0]), 0.05 * pf_[:, 2]], -1)
+               + 0.02 * rng.normal(size=(3000, 3)))
+    bad = rng.choice(3000, 60, replace=False)
+    vf_[bad] *= rng.uniform(3, 8, size=(60, 1))
+    dff = make_df(pf_, vf_)
+    outf = {"points": pf_, "values": vf_}
+    for kf, thr in ((25, 3.0), (10, 2.0), (24, 3.5)):
+        kept = rf.remove_outliers_knn(dff.copy(), k=kf, threshold=thr)
+        outf[f"kept_k{kf}_t{thr}"] = kept[["x", "y", "z", "u", "v", "w"]].values
+    np.savez_compressed(os.path.join(OUT, "case_f_filter.npz"), **outf)
     print("golden vectors written to", os.path.normpath(OUT))
 
 

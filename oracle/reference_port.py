@@ -25,7 +25,7 @@ __all__ = [
     "create_grid", "flat_coords", "knn_bruteforce", "knn_canonical", "idw_from_knn",
     "sibson_from_knn", "interpolate_field", "sample_mask_on_grid", "nearest_axis_index",
     "extract_boundary_particles", "compute_consistent_divergence", "flux_xy", "flux_xz",
-    "flux_yz", "mid_plane_x_flux", "mean_abs_div", "apply_mask_zero",
+    "flux_yz", "mid_plane_x_flux", "mean_abs_div", "apply_mask_zero", "outlier_keep_mask",
 ]
 
 
@@ -203,6 +203,23 @@ def apply_mask_zero(U, V, W, mask):
         a[~mask] = 0
         outs.append(a)
     return tuple(outs)
+
+
+# --------------------------------------------------------------------------- outlier filter (N1)
+def outlier_keep_mask(points, values, k=25, threshold=3.0, workers=1):
+    """filtering.py:5-58 restated: returns (keep_mask, kth_dist).  The self-query's first column is
+    dropped in the canonical (d2, index) order."""
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    u, v, w = values[:, 0], values[:, 1], values[:, 2]
+    speed = np.sqrt(u**2 + v**2 + w**2)
+    dist, idx, _ = knn_canonical(points, points, k + 1, workers=workers)
+    neighbor_indices = idx[:, 1:]
+    neighbor_distances = dist[:, 1:]
+    neighbor_speeds = speed[neighbor_indices]
+    local_medians = np.median(neighbor_speeds, axis=1)
+    local_mads = np.median(np.abs(neighbor_speeds - local_medians[:, np.newaxis]), axis=1)
+    z_scores = (np.abs(speed - local_medians)) / (local_mads + 1e-6)
+    return z_scores <= threshold, neighbor_distances[:, -1]
 
 
 # --------------------------------------------------------------------------- mask

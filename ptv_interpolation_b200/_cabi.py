@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PTV_OK, PTV_ERR_INVALID, PTV_ERR_TOO_FEW, PTV_ERR_CUDA, PTV_ERR_SINGULAR, PTV_ERR_NOMEM = range(6)
-METHOD_IDW, METHOD_SIBSON, METHOD_NEAREST, METHOD_RBF = range(4)
+METHOD_IDW, METHOD_SIBSON, METHOD_NEAREST, METHOD_RBF, METHOD_MADFILTER = range(5)
 F32, F64 = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -21,7 +21,7 @@ _lib = None
 
 EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
-    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons",
+    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_points", "ptv_outlier_filter",
     "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_interpolate_host",
 ]
@@ -56,6 +56,10 @@ def _declare(lib):
                                   C.POINTER(i32)]
     lib.ptv_knn_interp.restype = i32
     lib.ptv_knn_interp.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp, vp]
+    lib.ptv_knn_points.restype = i32
+    lib.ptv_knn_points.argtypes = [vp, vp, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp, vp]
+    lib.ptv_outlier_filter.restype = i32
+    lib.ptv_outlier_filter.argtypes = [vp, i32, f64, vp, vp, vp]
     lib.ptv_knn_stats.restype = i32
     lib.ptv_knn_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.ptv_knn_fail_reasons.restype = i32

@@ -34,6 +34,14 @@ struct KnnParams {
   const int* tile_list;  // heap kernel: process only these tiles (NULL = all tiles of the grid)
   const int* tile_count;
   unsigned long long* stats;  // optional counters (tiles, failed tiles, candidates, accepted)
+  // point-query mode (heap kernel): queries are the cell-sorted records of a second hash (or of the
+  // particle hash itself for self-queries); outputs are indexed by the query's original row
+  const ParticleRec* qrec;
+  int64_t nq;
+  // outlier filter (filtering.py:5-58): keep flag and distance to the k-th neighbour per particle
+  uint8_t* keep;
+  double* kth_dist;
+  double mad_threshold;
 };
 
 __device__ __forceinline__ bool key_greater(double ka, int ia, double kb, int ib) {
@@ -219,6 +227,91 @@ __device__ __forceinline__ int scan_shell(const HashGrid& g, const TileGeom& tg,
       body(m);
       __syncthreads();
     }
+  }
+  return staged;
+}
+
+// ---- pipelined variant used by the streaming kernel ---------------------------------------------
+// Two staging buffers; the records (and values) of chunk c+1 travel global -> shared with cp.async
+// (LDGSTS, no registers) while chunk c is being scanned, so the global-memory latency of staging is
+// hidden and each chunk costs one block barrier instead of two.
+static constexpr int kPipeCap = 128;  // records per pipelined chunk
+
+struct PipeBuf {
+  ParticleRec* stage64;  // [kPipeCap]
+  float4* stage32;       // [kPipeCap] tile-centre-relative float32 coordinates (converted on arrival)
+  void* stage_val;       // [kPipeCap] float4 / Value4
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int T, int kVal, typename F>
+__device__ __forceinline__ int scan_shell_pipe(const HashGrid& g, const TileGeom& tg, const RoundRegion& rg,
+                                               const RoundRegion& prev, bool have_prev, const PipeBuf (&buf)[2],
+                                               int* seg_start, int* seg_off, int* warp_tot, double cx, double cy,
+                                               double cz, F&& body) {
+  const int t = threadIdx.x;
+  const int nslots = region_slots(rg, have_prev);
+  int staged = 0;
+  for (int slot_base = 0; slot_base < nslots; slot_base += T) {
+    int start, cnt;
+    resolve_slot(g, tg, rg, prev, have_prev, slot_base + t, nslots, start, cnt);
+    int total;
+    const int off = block_scan_excl<T>(cnt, warp_tot, &total);
+    seg_start[t] = start;
+    seg_off[t] = off;
+    if (t == 0) seg_off[T] = total;
+    __syncthreads();
+    staged += total;
+    const int nchunks = (total + kPipeCap - 1) / kPipeCap;
+    auto issue = [&](int c) {  // asynchronous copies of chunk c into buffer c & 1
+      const PipeBuf& b = buf[c & 1];
+      const int m = min(kPipeCap, total - c * kPipeCap);
+      for (int j = t; j < m; j += T) {
+        const int gpos = c * kPipeCap + j;
+        int lo = 0, hi2 = T - 1;
+        while (lo < hi2) {  // record gpos lives in the last segment whose offset <= gpos
+          const int mid = (lo + hi2 + 1) >> 1;
+          if (seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
+        }
+        const int spos = seg_start[lo] + (gpos - seg_off[lo]);
+        const char* src = reinterpret_cast<const char*>(g.rec + spos);
+        char* dst = reinterpret_cast<char*>(b.stage64 + j);
+        cp_async16(dst, src);
+        cp_async16(dst + 16, src + 16);
+        if (kVal == 1) cp_async16(reinterpret_cast<float4*>(b.stage_val) + j, g.vals_s32 + spos);
+        if (kVal == 2) {
+          const char* vs = reinterpret_cast<const char*>(g.vals_s64 + spos);
+          char* vd = reinterpret_cast<char*>(reinterpret_cast<Value4*>(b.stage_val) + j);
+          cp_async16(vd, vs);
+          cp_async16(vd + 16, vs + 16);
+        }
+      }
+    };
+    if (nchunks > 0) issue(0);
+    for (int c = 0; c < nchunks; ++c) {
+      const PipeBuf& b = buf[c & 1];
+      const int m = min(kPipeCap, total - c * kPipeCap);
+      cp_async_commit_wait_all();  // this thread's copies of chunk c have landed
+      for (int j = t; j < ((m + 63) & ~63); j += T) {
+        if (j < m) {
+          const ParticleRec r = b.stage64[j];
+          b.stage32[j] = make_float4((float)(r.x - cx), (float)(r.y - cy), (float)(r.z - cz), 0.0f);
+        } else {
+          b.stage32[j] = make_float4(1e30f, 1e30f, 1e30f, 0.0f);  // far-away sentinel padding
+        }
+      }
+      __syncthreads();
+      if (c + 1 < nchunks) issue(c + 1);
+      body(b, m);
+    }
+    __syncthreads();  // seg_* and the buffers are rewritten by the next batch
   }
   return staged;
 }

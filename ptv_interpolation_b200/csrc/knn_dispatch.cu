@@ -69,6 +69,7 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   p.rscale = tuning().rscale;
   p.err_flag = h->err_flag;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
+  p.qrec = nullptr; p.nq = 0; p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
   p.tiles_x = p.tiles_y = p.tiles_z = 0;
   if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
 
@@ -117,6 +118,99 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
     if (*h->err_host != 0) { set_error("Singular matrix."); return PTV_ERR_SINGULAR; }
   }
   return PTV_OK;
+}
+
+static void init_point_params(KnnParams& p, const ptv_hash* h, const ptv_hash* q) {
+  p.g = h->view();
+  p.ax = p.ay = p.az = nullptr;
+  p.nx = p.ny = p.nz = 1;
+  p.mask = nullptr;
+  p.power = 2.0;
+  p.u = p.v = p.w = nullptr;
+  p.knn_idx = nullptr; p.knn_dist = nullptr;
+  p.tiles_x = p.tiles_y = p.tiles_z = 0;
+  p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
+  p.rscale = tuning().rscale;
+  p.smoothing = 0.0;
+  p.err_flag = h->err_flag;
+  p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
+  p.qrec = q->rec; p.nq = q->n;
+  p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
+}
+
+static int pick_heap_tile(int k, int method) {
+  const size_t smem_max = 227 * 1024;
+  int T = 128;
+  while (T > 32 && knn_heap_smem_bytes(T, k, method) > smem_max / 2) T >>= 1;
+  return knn_heap_smem_bytes(T, k, method) > smem_max ? 0 : T;
+}
+
+extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int method, int k, double idw_power,
+                              double rbf_smoothing, int out_dtype, void* d_u, void* d_v, void* d_w,
+                              int64_t* d_knn_idx, double* d_knn_dist, void* stream_) {
+  if (!h || !h->built || !queries || !queries->built) { set_error("ptv_knn_points: hash not built"); return PTV_ERR_INVALID; }
+  const bool want_uvw = d_u || d_v || d_w;
+  if (want_uvw && !(d_u && d_v && d_w)) { set_error("ptv_knn_points: give all of u, v, w or none"); return PTV_ERR_INVALID; }
+  if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_points: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
+  if (!want_uvw && !d_knn_idx) { set_error("ptv_knn_points: nothing to compute"); return PTV_ERR_INVALID; }
+  if (method == PTV_METHOD_NEAREST) k = 1;
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST &&
+      method != PTV_METHOD_RBF) { set_error("ptv_knn_points: unsupported method"); return PTV_ERR_INVALID; }
+  if (method == PTV_METHOD_RBF) {
+    if ((int64_t)k > h->n) k = (int)h->n;
+    if (k < 4) { set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3."); return PTV_ERR_INVALID; }
+    if (k + 4 > 32) { set_error("ptv_knn_points: rbf_neighbors > 28 is not supported on the CUDA path"); return PTV_ERR_INVALID; }
+  }
+  if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_points: bad out_dtype"); return PTV_ERR_INVALID; }
+  if (k < 1) { set_error("ptv_knn_points: k must be >= 1"); return PTV_ERR_INVALID; }
+  if ((int64_t)k > h->n) {
+    set_error("index " + std::to_string(h->n) + " is out of bounds for axis 0 with size " + std::to_string(h->n));
+    return PTV_ERR_TOO_FEW;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KnnParams p;
+  init_point_params(p, h, queries);
+  p.method = method; p.k = k; p.power = idw_power; p.smoothing = rbf_smoothing;
+  // u, v, w are always written by the kernel: give it scratch when only the lists are wanted
+  void* scratch = nullptr;
+  if (!want_uvw) {
+    PTV_CUDA(cudaMalloc(&scratch, (size_t)queries->n * 8 * 3));
+    d_u = scratch; d_v = (char*)scratch + (size_t)queries->n * 8; d_w = (char*)scratch + (size_t)queries->n * 16;
+  }
+  p.u = d_u; p.v = d_v; p.w = d_w;
+  p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
+  const int T = pick_heap_tile(k, method);
+  if (T == 0) { cudaFree(scratch); set_error("ptv_knn_points: k too large for shared memory (max ~580)"); return PTV_ERR_INVALID; }
+  if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
+  const_cast<ptv_hash*>(h)->last_used_stream = false;
+  int rc = launch_knn_heap(p, T, out_dtype == PTV_F32, stream);
+  if (rc == PTV_OK && method == PTV_METHOD_RBF) {
+    cudaError_t e = cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "ptv_knn_points", __FILE__, __LINE__);
+    else if (*h->err_host != 0) { set_error("Singular matrix."); rc = PTV_ERR_SINGULAR; }
+  }
+  if (scratch) { cudaStreamSynchronize(stream); cudaFree(scratch); }
+  return rc;
+}
+
+extern "C" int ptv_outlier_filter(const ptv_hash* h, int k, double threshold, uint8_t* d_keep, double* d_kth_dist,
+                                  void* stream_) {
+  if (!h || !h->built || !d_keep || !d_kth_dist) { set_error("ptv_outlier_filter: NULL argument / hash not built"); return PTV_ERR_INVALID; }
+  if (k < 1) { set_error("ptv_outlier_filter: k must be >= 1"); return PTV_ERR_INVALID; }
+  if (h->n <= k) {  // filtering.py:12-14 skips the filter; the shim never gets here
+    set_error("ptv_outlier_filter: fewer than k+1 particles");
+    return PTV_ERR_TOO_FEW;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KnnParams p;
+  init_point_params(p, h, h);
+  p.method = PTV_METHOD_MADFILTER; p.k = k + 1;  // the particle itself is its own nearest neighbour
+  p.keep = d_keep; p.kth_dist = d_kth_dist; p.mad_threshold = threshold;
+  const int T = pick_heap_tile(k + 1, p.method);
+  if (T == 0) { set_error("ptv_outlier_filter: k too large for shared memory"); return PTV_ERR_INVALID; }
+  const_cast<ptv_hash*>(h)->last_used_stream = false;
+  return launch_knn_heap(p, T, true, stream);
 }
 
 extern "C" int ptv_knn_fail_reasons(const ptv_hash* hc, int64_t reasons[4]) {

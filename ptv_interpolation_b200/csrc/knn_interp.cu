@@ -218,15 +218,30 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
   int* hi = hidx_all + t;
 
   const HashGrid& g = p.g;
-  const int tx = tile % p.tiles_x;
-  const int ty = (tile / p.tiles_x) % p.tiles_y;
-  const int tz = tile / (p.tiles_x * p.tiles_y);
-  const int ix = tx * TX + (t % TX);
-  const int iy = ty * TY + ((t / TX) % TY);
-  const int iz = tz * TZ + (t / (TX * TY));
-  const bool valid = ix < p.nx && iy < p.ny && iz < p.nz;
-  const int64_t vox = valid ? ((int64_t)iz * p.ny + iy) * p.nx + ix : 0;
-  const bool active = valid && (p.mask == nullptr || p.mask[vox] != 0);
+  bool valid, active;
+  int64_t vox = 0;
+  double qx = 0.0, qy = 0.0, qz = 0.0;
+  if (p.qrec != nullptr) {  // point-query mode: T consecutive cell-sorted query records
+    const int64_t qi = (int64_t)tile * T + t;
+    valid = qi < p.nq;
+    if (valid) {
+      const ParticleRec r = p.qrec[qi];
+      qx = r.x; qy = r.y; qz = r.z;
+      vox = r.idx;
+    }
+    active = valid;
+  } else {
+    const int tx = tile % p.tiles_x;
+    const int ty = (tile / p.tiles_x) % p.tiles_y;
+    const int tz = tile / (p.tiles_x * p.tiles_y);
+    const int ix = tx * TX + (t % TX);
+    const int iy = ty * TY + ((t / TX) % TY);
+    const int iz = tz * TZ + (t / (TX * TY));
+    valid = ix < p.nx && iy < p.ny && iz < p.nz;
+    vox = valid ? ((int64_t)iz * p.ny + iy) * p.nx + ix : 0;
+    active = valid && (p.mask == nullptr || p.mask[vox] != 0);
+    if (valid) { qx = p.ax[ix]; qy = p.ay[iy]; qz = p.az[iz]; }
+  }
 
   if (!__syncthreads_or(active ? 1 : 0)) {  // tile entirely solid / outside: zero fill
     if (valid) {
@@ -242,10 +257,6 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
     }
     return;
   }
-
-  const double qx = valid ? p.ax[ix] : 0.0;
-  const double qy = valid ? p.ay[iy] : 0.0;
-  const double qz = valid ? p.az[iz] : 0.0;
 
   TileGeom tg;
   tile_geometry<T>(g, active, qx, qy, qz, red, tg);
@@ -349,6 +360,54 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
     }
   }
 
+  if (!kRbf && p.method == PTV_METHOD_MADFILTER) {
+    // filtering.py:26-48 on the k+1 self-query: drop the first neighbour of the canonical order (the
+    // particle itself), median and MAD of the remaining speeds, z-score against the particle's own
+    // speed.  The heap columns are reused as scratch for the sorted speeds.
+    auto speed_of = [&](int i) {
+      const Value4 val = g.vals[i];
+      return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(val.u, val.u), __dmul_rn(val.v, val.v)), __dmul_rn(val.w, val.w)));
+    };
+    int first = 0;
+    double kth = 0.0;
+    for (int j = 0; j < kk; ++j) {
+      if (key_greater(hk[first * T], hi[first * T], hk[j * T], hi[j * T])) first = j;
+      kth = fmax(kth, hk[j * T]);
+    }
+    const int m = kk - 1;
+    int n = 0;
+    for (int j = 0; j < kk; ++j) {  // insertion sort of the neighbour speeds into hk[0..m)
+      if (j == first) continue;
+      const double sp = speed_of(hi[j * T]);
+      int q = n++;
+      while (q > 0 && hk[(q - 1) * T] > sp) {
+        hk[q * T] = hk[(q - 1) * T];
+        --q;
+      }
+      hk[q * T] = sp;
+    }
+    const double med = (m & 1) ? hk[(m / 2) * T] : 0.5 * (hk[(m / 2 - 1) * T] + hk[(m / 2) * T]);
+    // absolute deviations, sorted again (they are not monotone in the sorted speeds)
+    for (int j = 0; j < m; ++j) {
+      const double dv = fabs(hk[j * T] - med);
+      hk[j * T] = dv;
+    }
+    for (int j = 1; j < m; ++j) {
+      const double dv = hk[j * T];
+      int q = j;
+      while (q > 0 && hk[(q - 1) * T] > dv) {
+        hk[q * T] = hk[(q - 1) * T];
+        --q;
+      }
+      hk[q * T] = dv;
+    }
+    const double mad = (m & 1) ? hk[(m / 2) * T] : 0.5 * (hk[(m / 2 - 1) * T] + hk[(m / 2) * T]);
+    const double z = fabs(speed_of((int)vox) - med) / (mad + 1e-6);
+    p.keep[vox] = z <= p.mad_threshold ? 1 : 0;
+    p.kth_dist[vox] = sqrt(kth);
+    return;
+  }
+
   if (kRbf) {
     // computed above
   } else if (p.method == PTV_METHOD_NEAREST || (p.method == PTV_METHOD_IDW && kk == 1)) {
@@ -444,6 +503,10 @@ static int launch_knn(KnnParams& p, cudaStream_t stream) {
   p.tiles_x = (p.nx + TX - 1) / TX;
   p.tiles_y = (p.ny + TY - 1) / TY;
   p.tiles_z = (p.nz + TZ - 1) / TZ;
+  if (p.qrec != nullptr) {
+    p.tiles_x = (int)((p.nq + T - 1) / T);
+    p.tiles_y = p.tiles_z = 1;
+  }
   const int64_t ntiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
   if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
   const size_t smem = knn_heap_smem_bytes(T, p.k, p.method);

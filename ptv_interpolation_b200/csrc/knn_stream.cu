@@ -26,7 +26,7 @@ namespace ptv {
 static constexpr int kNB = 48;        // histogram bins over [0, Tmax)
 static constexpr int kListCap = 20;   // capacity of the crossing-bin list
 static constexpr int kMinEstimate = 16;
-static constexpr int kExactCap = 128;  // chunk size of the exact passes (two 64-bit accept masks)
+static_assert(kPipeCap == 128, "the exact passes use two 64-bit accept masks per chunk");
 
 // Values staged next to the candidates: float32 when the output is float32 (rounding 6e-8 relative,
 // far inside the 1e-5 bar), float64 when the caller asked for float64 output.
@@ -56,17 +56,16 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   int* lidx_all = reinterpret_cast<int*>(lkey_all + (size_t)kListCap * T);      // [kListCap][T]
   int* hist_all = reinterpret_cast<int*>(smem_raw);                             // [kNB][T] (alias)
   static_assert(kNB * 4 <= kListCap * 12, "histogram must fit under the list");
-  ParticleRec* stage64 = reinterpret_cast<ParticleRec*>(lidx_all + (size_t)kListCap * T);
-  float4* stage32 = reinterpret_cast<float4*>(stage64 + kStageCap);
   using ValT = typename StageVal<OutT>::type;  // float4 for float32 output, Value4 for float64 output
   constexpr int kVal = StageVal<OutT>::kind;
-  ValT* stage_val = reinterpret_cast<ValT*>(stage32 + kStageCap);
-  double* red = reinterpret_cast<double*>(stage_val + kStageCap);               // [6][NW]
+  ParticleRec* s64 = reinterpret_cast<ParticleRec*>(lidx_all + (size_t)kListCap * T);  // [2][kPipeCap]
+  ValT* sval = reinterpret_cast<ValT*>(s64 + 2 * kPipeCap);                             // [2][kPipeCap]
+  float4* s32 = reinterpret_cast<float4*>(sval + 2 * kPipeCap);                         // [2][kPipeCap]
+  double* red = reinterpret_cast<double*>(s32 + 2 * kPipeCap);                          // [6][NW]
   int* seg_start = reinterpret_cast<int*>(red + 6 * NW);
   int* seg_off = seg_start + T;
   int* warp_tot = seg_off + T + 1;
-  const ScanSmem sm{stage64, stage32, stage_val, seg_start, seg_off, warp_tot};
-
+  const PipeBuf pbuf[2] = {{s64, s32, sval}, {s64 + kPipeCap, s32 + kPipeCap, sval + kPipeCap}};
   uint16_t* vlist = reinterpret_cast<uint16_t*>(warp_tot + NW + 1);  // [4*T] compacted active voxels
 
   const int t = threadIdx.x;
@@ -170,8 +169,10 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     const bool last = R >= tg.rmax;
     if (last) R = tg.rmax;
     rg = make_region(g, tg, R);
-    scan_shell<T, kStageCap, true, false, 0, false>(g, tg, rg, prev, have_prev, sm, cx, cy, cz, [&](int m) {
+    scan_shell_pipe<T, 0>(g, tg, rg, prev, have_prev, pbuf, seg_start, seg_off, warp_tot, cx, cy, cz,
+                          [&](const PipeBuf& pb, int m) {
       if (active) {
+        const float4* stage32 = pb.stage32;
 #pragma unroll 4
         for (int j = 0; j < m; ++j) {
           const float4 c = stage32[j];
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   };
   // float32 pre-test of one 64-candidate half chunk -> bit mask of the candidates that need the
   // exact float64 key (the staged chunk is padded with far-away sentinels)
-  auto prefilter64 = [&](int base, float lim) {
+  auto prefilter64 = [&](const float4* stage32, int base, float lim) {
     unsigned long long msk = 0ULL;
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
@@ -263,22 +264,26 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     }
     return msk;
   };
-  auto exact_d2 = [&](int j) {
+  auto exact_d2 = [&](const ParticleRec* stage64, int j) {
     const double2 xy = *reinterpret_cast<const double2*>(&stage64[j].x);
     const double zz = stage64[j].z;
     const double ex = qx - xy.x, ey = qy - xy.y, ez = qz - zz;
     return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
   };
-  scan_shell<T, kExactCap, true, true, kVal, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
+  scan_shell_pipe<T, kVal>(g, tg, rg, rg, false, pbuf, seg_start, seg_off, warp_tot, cx, cy, cz,
+                           [&](const PipeBuf& pb, int m) {
     if (active) {
-      unsigned long long m0 = prefilter64(0, hi32);
-      unsigned long long m1 = m > 64 ? prefilter64(64, hi32) : 0ULL;
+      const float4* stage32 = pb.stage32;
+      const ParticleRec* stage64 = pb.stage64;
+      const ValT* stage_val = reinterpret_cast<const ValT*>(pb.stage_val);
+      unsigned long long m0 = prefilter64(stage32, 0, hi32);
+      unsigned long long m1 = m > 64 ? prefilter64(stage32, 64, hi32) : 0ULL;
       // each thread walks only ITS accepted candidates (dense per lane instead of "any lane")
       while ((m0 | m1) != 0ULL) {
         int j;
         if (m0 != 0ULL) { j = __ffsll((long long)m0) - 1; m0 &= m0 - 1ULL; }
         else { j = 64 + __ffsll((long long)m1) - 1; m1 &= m1 - 1ULL; }
-        const double d2 = exact_d2(j);
+        const double d2 = exact_d2(stage64, j);
         if (d2 < e_lo) {
           ++n_in;
           if (sib) {
@@ -361,15 +366,19 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
         sib_acc(lkey[i * T], val.u, val.v, val.w);
       }
     const float lo32 = (float)((e_lo + 16.0 * sqrt(e_lo) * ec + 64.0 * ec * ec) * (1.0 + 1e-5));
-    scan_shell<T, kExactCap, true, true, kVal, true>(g, tg, rg, rg, false, sm, cx, cy, cz, [&](int m) {
+    scan_shell_pipe<T, kVal>(g, tg, rg, rg, false, pbuf, seg_start, seg_off, warp_tot, cx, cy, cz,
+                             [&](const PipeBuf& pb, int m) {
       if (active) {
-        unsigned long long m0 = prefilter64(0, lo32);
-        unsigned long long m1 = m > 64 ? prefilter64(64, lo32) : 0ULL;
+        const float4* stage32 = pb.stage32;
+        const ParticleRec* stage64 = pb.stage64;
+        const ValT* stage_val = reinterpret_cast<const ValT*>(pb.stage_val);
+        unsigned long long m0 = prefilter64(stage32, 0, lo32);
+        unsigned long long m1 = m > 64 ? prefilter64(stage32, 64, lo32) : 0ULL;
         while ((m0 | m1) != 0ULL) {
           int j;
           if (m0 != 0ULL) { j = __ffsll((long long)m0) - 1; m0 &= m0 - 1ULL; }
           else { j = 64 + __ffsll((long long)m1) - 1; m1 &= m1 - 1ULL; }
-          const double d2 = exact_d2(j);
+          const double d2 = exact_d2(stage64, j);
           if (d2 < e_lo) {
             const ValT val = stage_val[j];
             sib_acc(d2, (double)StageVal<OutT>::u(val), (double)StageVal<OutT>::v(val),
@@ -398,7 +407,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
 static size_t stream_smem_bytes(int T, bool f32) {
   const int NW = T / 32;
   size_t b = (size_t)kListCap * T * 12 +
-             (size_t)kStageCap * (sizeof(ParticleRec) + sizeof(float4) + (f32 ? sizeof(float4) : sizeof(Value4))) +
+             (size_t)2 * kPipeCap * (sizeof(ParticleRec) + sizeof(float4) + (f32 ? sizeof(float4) : sizeof(Value4))) +
              (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 2 + NW) * sizeof(int) + (size_t)4 * T * sizeof(uint16_t);
   return (b + 15) & ~(size_t)15;
 }

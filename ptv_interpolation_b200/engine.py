@@ -157,6 +157,41 @@ class PTVEngine:
                     host_out[c, a:b].copy_(dev_out[c, a:b], non_blocking=True)
         return dev_out
 
+    def interpolate_points(self, queries: "PTVEngine", method="idw", k=50, idw_power=2.0, smoothing=0.0,
+                           out_dtype=torch.float32, return_knn=False, values=True):
+        """The same search / weights for arbitrary query points: ``queries`` is a second engine whose
+        hash was built over the query points (pass ``self`` for a self-query).  Returns a (3, nq) tensor
+        indexed by the query's original row (and (dist, idx) (nq,k) if ``return_knn``)."""
+        if method not in _METHODS:
+            raise NotImplementedError(f"method {method!r} is not on the CUDA path")
+        nq = queries.n_particles
+        if method == "nearest":
+            k = 1
+        out = torch.empty((3, nq), dtype=out_dtype, device=self.device) if values else None
+        kd = ki = None
+        if return_knn:
+            ki = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            kd = torch.empty((nq, k), dtype=torch.float64, device=self.device)
+        o = [None, None, None] if out is None else [out[0], out[1], out[2]]
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_knn_points(self._h, queries._h, _METHODS[method], int(k), float(idw_power),
+                                                float(smoothing), _dtype_code(out_dtype), _ptr(o[0]), _ptr(o[1]),
+                                                _ptr(o[2]), _ptr(ki), _ptr(kd), self._stream()))
+        if return_knn:
+            return out, kd, ki
+        return out
+
+    def outlier_filter(self, k=25, threshold=3.0):
+        """kNN median/MAD filter on the particles of the current hash (filtering.py:5-58).  Returns
+        (keep uint8 (Np,), kth_dist float64 (Np,)) CUDA tensors."""
+        n = self.n_particles
+        keep = torch.empty(n, dtype=torch.uint8, device=self.device)
+        kth = torch.empty(n, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_outlier_filter(self._h, int(k), float(threshold), _ptr(keep), _ptr(kth),
+                                                    self._stream()))
+        return keep, kth
+
     def knn_stats(self):
         """Diagnostics of the last interpolate(): did the streaming kernel run, how many tiles fell
         back to the exact heap kernel, how many it finished itself (needs set_tuning(stats=1))."""

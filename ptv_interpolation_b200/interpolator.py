@@ -88,8 +88,7 @@ def _grid_axes(grid_tuple):
               and np.array_equal(Y, np.broadcast_to(Y[0:1, :, 0:1], Y.shape))
               and np.array_equal(Z, np.broadcast_to(Z[:, 0:1, 0:1], Z.shape)))
         if not ok:
-            raise NotImplementedError("interpolate_field: only rectilinear (meshgrid) query grids are "
-                                      "on the CUDA path")
+            return None  # arbitrary query points: handled by the point-query kernel
     return x, y, z
 
 
@@ -107,9 +106,13 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
             f"CUDA path; supported methods: {_GPU_METHODS}")
     if method == "rbf" and rbf_kernel != "thin_plate_spline":
         raise NotImplementedError("only rbf_kernel='thin_plate_spline' is on the CUDA path")
-    x, y, z = _grid_axes(grid_tuple)
+    axes = _grid_axes(grid_tuple)
     eng = default_engine(device)
     dev = eng.device
+    if axes is None:
+        return _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,
+                                      idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn)
+    x, y, z = axes
     pts = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev)
     vals = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
     k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors}[method]
@@ -132,6 +135,48 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     torch.cuda.synchronize(dev)
     host = host_t.numpy()
     return host[0], host[1], host[2]
+
+
+def _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,
+                           idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn):
+    """interpolate_field for a grid_tuple that is not a rectilinear meshgrid: the (X, Y, Z) arrays are
+    treated as arbitrary query points (what the reference does with every grid, interpolator.py:93)."""
+    import torch
+    from .engine import PTVEngine
+    dev = eng.device
+    X, Y, Z = (np.asarray(a, dtype=np.float64) for a in grid_tuple)
+    shape = X.shape
+    q = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=-1)
+    sel = None
+    if mask is not None:
+        sel = np.flatnonzero(np.asarray(mask).ravel() != 0)
+        q = q[sel]
+    k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors}[method]
+    if method == "rbf":
+        k = min(int(k), len(points))
+    tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
+    eng.build(torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev),
+              torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev))
+    full = np.zeros((3,) + shape, dtype=out_dtype)
+    kd = ki = None
+    if len(q):
+        qe = PTVEngine(dev)
+        qt = torch.from_numpy(np.ascontiguousarray(q)).to(dev)
+        qe.build(qt, qt)
+        res = eng.interpolate_points(qe, method=method, k=int(k), idw_power=float(idw_power),
+                                     smoothing=float(smoothing), out_dtype=tdt, return_knn=return_knn)
+        out = res[0] if return_knn else res
+        flat = full.reshape(3, -1)
+        if sel is None:
+            flat[:] = out.cpu().numpy()
+        else:
+            flat[:, sel] = out.cpu().numpy()
+        if return_knn:
+            kd, ki = res[1].cpu().numpy(), res[2].cpu().numpy()
+        qe.close()
+    if return_knn:
+        return full[0], full[1], full[2], kd, ki
+    return full[0], full[1], full[2]
 
 
 def _nearest_axis_index(src_coords, q):

@@ -482,3 +482,61 @@ def test_c3_size_sibson_sampled_voxels_vs_oracle():
     ref = rp.sibson_from_knn(d, i, vals).T
     got = out.reshape(3, -1)[:, sel].cpu().numpy()
     _assert_vel(got[:, None, None, :], ref[:, None, None, :], vals)
+
+
+# ------------------------------------------------------------------ N1: outlier filter + point queries
+@pytest.mark.parametrize("k,thr", [(25, 3.0), (10, 2.0), (24, 3.5)])
+def test_outlier_filter_golden(golden_dir, k, thr):
+    from ptv_interpolation_b200 import filtering as gf
+    g = np.load(os.path.join(golden_dir, "case_f_filter.npz"))
+    kept = gf.remove_outliers_knn(_df(g["points"], g["values"]), k=k, threshold=thr)
+    assert np.array_equal(kept[["x", "y", "z", "u", "v", "w"]].values, g[f"kept_k{k}_t{thr}"])
+    # kth-neighbour distances (the "filtering radius" report) and the too-small-frame path
+    eng = PTVEngine()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    eng.build(t(g["points"]), t(g["values"]))
+    keep, kth = eng.outlier_filter(k=k, threshold=thr)
+    rk, rkth = rp.outlier_keep_mask(g["points"], g["values"], k, thr)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), rk) and np.array_equal(kth.cpu().numpy(), rkth)
+    small = _df(g["points"][:5], g["values"][:5])
+    assert gf.remove_outliers_knn(small, k=k) is small
+
+
+def test_apply_filters_namespace():
+    import types
+    from ptv_interpolation_b200 import filtering as gf
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(0, 10, size=(500, 3))
+    vals = rng.normal(size=(500, 3))
+    vals[7] = 50.0
+    df = _df(pts, vals)
+    args = types.SimpleNamespace(filter_outliers=False, filter_max_speed=10.0, filter_neighbors=20, filter_threshold=3.0)
+    assert gf.apply_filters(df, args) is df
+    args.filter_outliers = True
+    out = gf.apply_filters(df, args)
+    thr = df[np.sqrt((df[["u", "v", "w"]].values ** 2).sum(1)) <= 10.0].reset_index(drop=True)
+    rk, _ = rp.outlier_keep_mask(thr[["x", "y", "z"]].values, thr[["u", "v", "w"]].values, 20, 3.0)
+    assert np.array_equal(out.values, thr[rk].values)
+
+
+@pytest.mark.parametrize("method,k", [("idw", 12), ("sibson", 30), ("rbf", 20), ("nearest", 1)])
+def test_scattered_query_points(method, k):
+    """A grid_tuple that is NOT a rectilinear meshgrid (jittered coordinates): the reference treats
+    every grid as a point list (interpolator.py:93); so does the point-query kernel."""
+    rng = np.random.default_rng(31)
+    pts = rng.uniform(0, 12, size=(2500, 3)).astype(np.float32).astype(np.float64)
+    vals = rng.normal(size=(2500, 3))
+    og, _ = rp.create_grid(((0, 12), (0, 12), (0, 12)), (9, 8, 7))
+    grid = tuple(a + 0.3 * rng.random(a.shape) for a in og)
+    kw = dict(method=method, idw_neighbors=k, sibson_neighbors=k, rbf_neighbors=k)
+    res = gi.interpolate_field(_df(pts, vals), grid, out_dtype=np.float64, return_knn=(method != "rbf"), **kw)
+    ref = rp.interpolate_field(pts, vals, grid, return_knn=(method in ("idw", "sibson")), **kw)
+    _assert_vel(np.stack(res[:3]), np.stack(ref[:3]), vals)
+    if method in ("idw", "sibson"):
+        assert np.array_equal(res[4], ref[4]) and np.array_equal(res[3], ref[3])
+    # with a mask only the pore points are queried
+    m = rng.random(grid[0].shape) > 0.5
+    U, V, W = gi.interpolate_field(_df(pts, vals), grid, mask=m, out_dtype=np.float64, **kw)
+    full = np.stack(res[:3])
+    assert np.all(np.stack([U, V, W])[:, ~m] == 0)
+    assert np.abs(np.stack([U, V, W])[:, m] - full[:, m]).max() <= 1e-11 * np.abs(full).max()

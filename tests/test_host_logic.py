@@ -66,8 +66,8 @@ def test_create_grid_matches_reference_port(bounds, res):
     assert all(np.array_equal(a, b) for a, b in zip(ax, (x, y, z)))
     ax = gi._grid_axes((Xr, Yr, Zr))  # dense meshgrid is verified, not assumed
     assert all(np.array_equal(a, b) for a, b in zip(ax, (x, y, z)))
-    with pytest.raises(NotImplementedError):
-        gi._grid_axes((Xr + np.random.default_rng(0).random(Xr.shape), Yr, Zr))
+    # anything else is treated as arbitrary query points (point-query kernel)
+    assert gi._grid_axes((Xr + np.random.default_rng(0).random(Xr.shape), Yr, Zr)) is None
 
 
 def test_nearest_axis_index_matches_oracle():

@@ -120,3 +120,11 @@ def test_reference_own_test_shape(golden_dir):
     grid, _ = rp.create_grid(((0, 10), (0, 10), (0, 10)), 10)
     U, V, W = rp.interpolate_field(pts, vals, grid, method="rbf")
     assert np.array_equal(np.stack([U, V, W], 0), g["uvw"])
+
+
+@pytest.mark.parametrize("k,thr", [(25, 3.0), (10, 2.0), (24, 3.5)])
+def test_outlier_filter_port(golden_dir, k, thr):
+    g = _load(golden_dir, "case_f_filter.npz")
+    keep, kth = rp.outlier_keep_mask(g["points"], g["values"], k, thr)
+    got = np.concatenate([g["points"], g["values"]], 1)[keep]
+    assert np.array_equal(got, g[f"kept_k{k}_t{thr}"])
