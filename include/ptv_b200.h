@@ -156,6 +156,13 @@ int ptv_divergence_flux(const void* d_u, const void* d_v, const void* d_w, const
                         const void* d_w_above, const uint8_t* d_mask_above, int dtype, void* d_div,
                         double* d_absdiv_sum, double* d_qxy, double* d_qxz, double* d_qyz, void* stream);
 
+/* ---- shear-rate magnitude and vorticity magnitude: replaces compute_strain_rate / compute_vorticity
+ *      (velocity_analysis.py:10-63, 94-120; nine np.gradient stencils).  d_mask nullable; either output
+ *      nullable. ------------------------------------------------------------------------------- */
+int ptv_strain_vorticity(const void* d_u, const void* d_v, const void* d_w, const uint8_t* d_mask, int nx,
+                         int ny, int nz, double dx, double dy, double dz, int dtype, void* d_strain,
+                         void* d_vorticity, void* stream);
+
 /* ---- host-buffer convenience (what a non-CUDA caller binds): copies in, runs
  *      ptv_hash_build + ptv_knn_interp, copies out.  All pointers are HOST pointers. ------ */
 int ptv_interpolate_host(const double* h_points, const double* h_values, int64_t n,

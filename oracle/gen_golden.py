@@ -158,6 +158,20 @@ def main():
         kept = rf.remove_outliers_knn(dff.copy(), k=kf, threshold=thr)
         outf[f"kept_k{kf}_t{thr}"] = kept[["x", "y", "z", "u", "v", "w"]].values
     np.savez_compressed(os.path.join(OUT, "case_f_filter.npz"), **outf)
+    # ---- case G: strain rate / vorticity / dissipation (velocity_analysis.py:10-120)
+    sys.path.insert(0, REF)
+    import velocity_analysis as va
+    sys.path.pop(0)
+    rng = np.random.default_rng(707)
+    shape = (9, 8, 10)
+    ug, vg, wg = (rng.normal(size=shape) for _ in range(3))
+    mg = rng.random(shape) > 0.3
+    hs = (1.25, 0.75, 2.0)
+    sr = va.compute_strain_rate(ug, vg, wg, *hs, mask=mg)
+    np.savez_compressed(os.path.join(OUT, "case_g_analysis.npz"), u=ug, v=vg, w=wg, mask=mg, h=np.array(hs),
+                        strain=sr, strain_nomask=va.compute_strain_rate(ug, vg, wg, 1.0, 1.0, 1.0),
+                        vort=va.compute_vorticity(ug, vg, wg, *hs, mask=mg),
+                        diss=va.compute_viscous_dissipation(sr.copy(), 1.3e-3, mask=mg))
     print("golden vectors written to", os.path.normpath(OUT))
 
 

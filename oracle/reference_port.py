@@ -25,7 +25,7 @@ __all__ = [
     "create_grid", "flat_coords", "knn_bruteforce", "knn_canonical", "idw_from_knn",
     "sibson_from_knn", "interpolate_field", "sample_mask_on_grid", "nearest_axis_index",
     "extract_boundary_particles", "compute_consistent_divergence", "flux_xy", "flux_xz",
-    "flux_yz", "mid_plane_x_flux", "mean_abs_div", "apply_mask_zero", "outlier_keep_mask",
+    "flux_yz", "mid_plane_x_flux", "mean_abs_div", "apply_mask_zero", "outlier_keep_mask", "compute_strain_rate", "compute_vorticity",
 ]
 
 
@@ -203,6 +203,31 @@ def apply_mask_zero(U, V, W, mask):
         a[~mask] = 0
         outs.append(a)
     return tuple(outs)
+
+
+# --------------------------------------------------------------------------- gradient stencils (N3)
+def compute_strain_rate(u, v, w, dx, dy, dz, mask=None):
+    """velocity_analysis.py:10-63."""
+    du_dz, du_dy, du_dx = np.gradient(u, dz, dy, dx)
+    dv_dz, dv_dy, dv_dx = np.gradient(v, dz, dy, dx)
+    dw_dz, dw_dy, dw_dx = np.gradient(w, dz, dy, dx)
+    exx, eyy, ezz = 2 * du_dx, 2 * dv_dy, 2 * dw_dz
+    exy, exz, eyz = du_dy + dv_dx, du_dz + dw_dx, dv_dz + dw_dy
+    s = np.sqrt(0.5 * (exx**2 + eyy**2 + ezz**2) + exy**2 + exz**2 + eyz**2)
+    if mask is not None:
+        s[~mask] = 0.0
+    return s
+
+
+def compute_vorticity(u, v, w, dx, dy, dz, mask=None):
+    """velocity_analysis.py:94-120."""
+    du_dz, du_dy, du_dx = np.gradient(u, dz, dy, dx)
+    dv_dz, dv_dy, dv_dx = np.gradient(v, dz, dy, dx)
+    dw_dz, dw_dy, dw_dx = np.gradient(w, dz, dy, dx)
+    o = np.sqrt((dw_dy - dv_dz)**2 + (du_dz - dw_dx)**2 + (dv_dx - du_dy)**2)
+    if mask is not None:
+        o[~mask] = 0.0
+    return o
 
 
 # --------------------------------------------------------------------------- outlier filter (N1)

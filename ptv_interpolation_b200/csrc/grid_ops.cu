@@ -253,6 +253,95 @@ __global__ void __launch_bounds__(256) divergence_kernel(
   }
 }
 
+// ------------------------------------------------------------------ strain rate / vorticity (N3)
+// velocity_analysis.py:10-63 (compute_strain_rate) and :94-120 (compute_vorticity): nine np.gradient
+// derivatives (second-order central inside, first-order one-sided at the edges, uniform spacing),
+// then the shear-rate magnitude sqrt(0.5*(exx^2+eyy^2+ezz^2) + exy^2 + exz^2 + eyz^2) and |curl u|,
+// zeroed in solid voxels.  float64 arithmetic in NumPy's operation order (bit-identical for float64
+// fields).  HBM-bound: 13 B read + 4 B per output written per voxel.
+__device__ __forceinline__ double grad_div(double num, double den) {
+  if (num == 0.0) return den > 0.0 ? num : -num;  // signed zero without the division slow path
+  return __ddiv_rn(num, den);
+}
+
+template <typename Tf>
+__device__ __forceinline__ double np_gradient(const Tf* __restrict__ f, int64_t i, int64_t stride, int pos, int n,
+                                              double h) {
+  if (n == 1) return 0.0;  // never reached: np.gradient needs >= 2 points (checked on the host)
+  if (pos == 0) return grad_div(__dsub_rn((double)f[i + stride], (double)f[i]), h);
+  if (pos == n - 1) return grad_div(__dsub_rn((double)f[i], (double)f[i - stride]), h);
+  return grad_div(__dsub_rn((double)f[i + stride], (double)f[i - stride]), __dmul_rn(2.0, h));
+}
+
+template <typename Tf>
+__global__ void __launch_bounds__(256) strain_vorticity_kernel(const Tf* __restrict__ u, const Tf* __restrict__ v,
+                                                                const Tf* __restrict__ w,
+                                                                const uint8_t* __restrict__ mask, int nx, int ny, int nz,
+                                                                double dx, double dy, double dz,
+                                                                Tf* __restrict__ strain, Tf* __restrict__ vort) {
+  const int64_t n = (int64_t)nx * ny * nz;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask != nullptr && mask[i] == 0) {  // velocity_analysis.py:58-61,116-117
+    if (strain) strain[i] = (Tf)0;
+    if (vort) vort[i] = (Tf)0;
+    return;
+  }
+  const int x = (int)(i % nx);
+  const int y = (int)((i / nx) % ny);
+  const int z = (int)(i / ((int64_t)nx * ny));
+  const int64_t sy = nx, sz = (int64_t)nx * ny;
+  const double du_dx = np_gradient(u, i, 1, x, nx, dx), du_dy = np_gradient(u, i, sy, y, ny, dy),
+               du_dz = np_gradient(u, i, sz, z, nz, dz);
+  const double dv_dx = np_gradient(v, i, 1, x, nx, dx), dv_dy = np_gradient(v, i, sy, y, ny, dy),
+               dv_dz = np_gradient(v, i, sz, z, nz, dz);
+  const double dw_dx = np_gradient(w, i, 1, x, nx, dx), dw_dy = np_gradient(w, i, sy, y, ny, dy),
+               dw_dz = np_gradient(w, i, sz, z, nz, dz);
+  if (strain) {
+    const double exx = __dmul_rn(2.0, du_dx), eyy = __dmul_rn(2.0, dv_dy), ezz = __dmul_rn(2.0, dw_dz);
+    const double exy = __dadd_rn(du_dy, dv_dx), exz = __dadd_rn(du_dz, dw_dx), eyz = __dadd_rn(dv_dz, dw_dy);
+    const double diag = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(exx, exx), __dmul_rn(eyy, eyy)), __dmul_rn(ezz, ezz)));
+    const double s2 = __dadd_rn(__dadd_rn(__dadd_rn(diag, __dmul_rn(exy, exy)), __dmul_rn(exz, exz)), __dmul_rn(eyz, eyz));
+    strain[i] = (Tf)sqrt(s2);
+  }
+  if (vort) {
+    const double vx = __dsub_rn(dw_dy, dv_dz), vy = __dsub_rn(du_dz, dw_dx), vz = __dsub_rn(dv_dx, du_dy);
+    vort[i] = (Tf)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+  }
+}
+
+}  // namespace ptv
+
+using namespace ptv;
+
+extern "C" int ptv_strain_vorticity(const void* d_u, const void* d_v, const void* d_w, const uint8_t* d_mask, int nx,
+                                    int ny, int nz, double dx, double dy, double dz, int dtype, void* d_strain,
+                                    void* d_vorticity, void* stream) {
+  if (!d_u || !d_v || !d_w) { set_error("ptv_strain_vorticity: NULL argument"); return PTV_ERR_INVALID; }
+  if (!d_strain && !d_vorticity) { set_error("ptv_strain_vorticity: nothing to compute"); return PTV_ERR_INVALID; }
+  if (nx < 2 || ny < 2 || nz < 2) {
+    // np.gradient: "Shape of array too small to calculate a numerical gradient, at least 2 elements are required"
+    set_error("Shape of array too small to calculate a numerical gradient, at least (edge_order + 1) elements are required.");
+    return PTV_ERR_INVALID;
+  }
+  const int64_t n = (int64_t)nx * ny * nz;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (dtype == PTV_F32)
+    strain_vorticity_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dx, dy, dz, (float*)d_strain,
+        (float*)d_vorticity);
+  else if (dtype == PTV_F64)
+    strain_vorticity_kernel<double><<<nb, 256, 0, (cudaStream_t)stream>>>(
+        (const double*)d_u, (const double*)d_v, (const double*)d_w, d_mask, nx, ny, nz, dx, dy, dz, (double*)d_strain,
+        (double*)d_vorticity);
+  else { set_error("ptv_strain_vorticity: bad dtype"); return PTV_ERR_INVALID; }
+  count_launches(1);
+  PTV_CUDA(cudaGetLastError());
+  return PTV_OK;
+}
+
+namespace ptv {
+
 // ------------------------------------------------------------------ flux profiles (a13)
 // q_xy[z] += sum_{y,x} w   (plot_flux.py:6-8)
 template <typename Tf>

@@ -248,7 +248,11 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   // so the reciprocal runs on the SFU; float64 output keeps the IEEE division.
   auto idw_weight = [&](double d2) -> double {
     const double den = (p2 ? d2 : pow(sqrt(d2), p.power)) + eps;
-    if (sizeof(OutT) == 4 && p2) return (double)__frcp_rn((float)den);  // den in [1e-10, ~1e12]: float32-safe
+    if (sizeof(OutT) == 4 && p2) {  // den in [1e-10, ~1e12]: float32-safe; MUFU.RCP, 1 ulp
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)den));
+      return (double)r;
+    }
     return 1.0 / den;
   };
   // float32 pre-test of one 64-candidate half chunk -> bit mask of the candidates that need the

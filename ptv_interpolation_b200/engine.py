@@ -275,6 +275,20 @@ class PTVEngine:
                                                      _ptr(qxy), _ptr(qxz), _ptr(qyz), self._stream()))
         return div, stats, qxy, qxz, qyz
 
+    def strain_vorticity(self, u, v, w, dx, dy, dz, mask=None, strain=True, vorticity=True):
+        """(shear-rate magnitude, vorticity magnitude) of the field; either may be skipped (None)."""
+        nz, ny, nx = u.shape
+        if mask is not None and mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        u, v, w = u.contiguous(), v.contiguous(), w.contiguous()
+        s = torch.empty_like(u) if strain else None
+        o = torch.empty_like(u) if vorticity else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_strain_vorticity(_ptr(u), _ptr(v), _ptr(w), _ptr(mask), nx, ny, nz, float(dx),
+                                                      float(dy), float(dz), _dtype_code(u.dtype), _ptr(s), _ptr(o),
+                                                      self._stream()))
+        return s, o
+
     def flux_profiles(self, u, v, w):
         """Unscaled plane sums (q_xy[nz], q_xz[ny], q_yz[nx]) as float64 CUDA tensors."""
         ref = next(t for t in (u, v, w) if t is not None)

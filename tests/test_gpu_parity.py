@@ -540,3 +540,22 @@ def test_scattered_query_points(method, k):
     full = np.stack(res[:3])
     assert np.all(np.stack([U, V, W])[:, ~m] == 0)
     assert np.abs(np.stack([U, V, W])[:, m] - full[:, m]).max() <= 1e-11 * np.abs(full).max()
+
+
+# ------------------------------------------------------------------ N3: strain rate / vorticity stencils
+def test_strain_vorticity_golden(golden_dir):
+    from ptv_interpolation_b200 import velocity_analysis as gva
+    g = np.load(os.path.join(golden_dir, "case_g_analysis.npz"))
+    dx, dy, dz = (float(h) for h in g["h"])
+    s = gva.compute_strain_rate(g["u"], g["v"], g["w"], dx, dy, dz, mask=g["mask"])
+    assert s.dtype == np.float64 and np.array_equal(s, g["strain"])
+    assert np.array_equal(gva.compute_strain_rate(g["u"], g["v"], g["w"], 1.0, 1.0, 1.0), g["strain_nomask"])
+    assert np.array_equal(gva.compute_vorticity(g["u"], g["v"], g["w"], dx, dy, dz, mask=g["mask"]), g["vort"])
+    assert np.array_equal(gva.compute_viscous_dissipation(s.copy(), 1.3e-3, mask=g["mask"]), g["diss"])
+    u32, v32, w32 = (g[c].astype(np.float32) for c in "uvw")
+    s32 = gva.compute_strain_rate(u32, v32, w32, dx, dy, dz, mask=g["mask"])
+    ref = rp.compute_strain_rate(u32.astype(np.float64), v32.astype(np.float64), w32.astype(np.float64), dx, dy, dz,
+                                 mask=g["mask"])
+    assert s32.dtype == np.float32 and np.array_equal(s32, ref.astype(np.float32))
+    with pytest.raises(ValueError):
+        gva.compute_vorticity(np.zeros((1, 4, 4)), np.zeros((1, 4, 4)), np.zeros((1, 4, 4)), 1, 1, 1)

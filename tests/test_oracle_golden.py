@@ -128,3 +128,11 @@ def test_outlier_filter_port(golden_dir, k, thr):
     keep, kth = rp.outlier_keep_mask(g["points"], g["values"], k, thr)
     got = np.concatenate([g["points"], g["values"]], 1)[keep]
     assert np.array_equal(got, g[f"kept_k{k}_t{thr}"])
+
+
+def test_analysis_stencils_port(golden_dir):
+    g = _load(golden_dir, "case_g_analysis.npz")
+    dx, dy, dz = g["h"]
+    assert np.array_equal(rp.compute_strain_rate(g["u"], g["v"], g["w"], dx, dy, dz, mask=g["mask"]), g["strain"])
+    assert np.array_equal(rp.compute_strain_rate(g["u"], g["v"], g["w"], 1.0, 1.0, 1.0), g["strain_nomask"])
+    assert np.array_equal(rp.compute_vorticity(g["u"], g["v"], g["w"], dx, dy, dz, mask=g["mask"]), g["vort"])
