@@ -163,6 +163,21 @@ int ptv_strain_vorticity(const void* d_u, const void* d_v, const void* d_w, cons
                          int ny, int nz, double dx, double dy, double dz, int dtype, void* d_strain,
                          void* d_vorticity, void* stream);
 
+/* ---- projection cleaning (physics.py:55-209).  ptv_poisson_lsqr solves
+ *      A phi = div - mean(div[mask]) with the matrix-free masked 7-point Laplacian of
+ *      build_laplacian_matrix (physics.py:55-108) by LSQR with SciPy's recurrences and stopping rules
+ *      (physics.py:186: damp=1e-8, atol=btol=1e-10, iter_lim=3000; conlim SciPy default 1e8).
+ *      d_phi: float64 (nz,ny,nx), zero in solid voxels; d_work: ptv_poisson_workspace_bytes() bytes;
+ *      h_info[8] (host): istop, itn, r1norm, r2norm, anorm, acond, arnorm, xnorm.
+ *      ptv_projection_correct applies apply_consistent_correction (physics.py:110-147). ---------- */
+int64_t ptv_poisson_workspace_bytes(int nx, int ny, int nz);
+int ptv_poisson_lsqr(const void* d_div, int dtype, const uint8_t* d_mask, int nx, int ny, int nz, double dx,
+                     double dy, double dz, double damp, double atol, double btol, double conlim, int iter_lim,
+                     double* d_phi, void* d_work, double* h_info, void* stream);
+int ptv_projection_correct(const void* d_u, const void* d_v, const void* d_w, const double* d_phi,
+                           const uint8_t* d_mask, int nx, int ny, int nz, double dx, double dy, double dz,
+                           int dtype, void* d_uo, void* d_vo, void* d_wo, void* stream);
+
 /* ---- host-buffer convenience (what a non-CUDA caller binds): copies in, runs
  *      ptv_hash_build + ptv_knn_interp, copies out.  All pointers are HOST pointers. ------ */
 int ptv_interpolate_host(const double* h_points, const double* h_values, int64_t n,

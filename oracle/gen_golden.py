@@ -172,6 +172,26 @@ def main():
                         strain=sr, strain_nomask=va.compute_strain_rate(ug, vg, wg, 1.0, 1.0, 1.0),
                         vort=va.compute_vorticity(ug, vg, wg, *hs, mask=mg),
                         diss=va.compute_viscous_dissipation(sr.copy(), 1.3e-3, mask=mg))
+    # ---- case H: projection cleaning (physics.py:149-209): Laplacian, lsqr, correction, 3 iterations
+    import contextlib, io
+    rng = np.random.default_rng(808)
+    shape = (12, 11, 10)
+    zz, yy, xx = np.meshgrid(*(np.arange(s_, dtype=float) for s_ in shape), indexing="ij")
+    mh = ((xx - 4.5) ** 2 + (yy - 5.0) ** 2 + (zz - 6.0) ** 2) > 2.7 ** 2
+    mh &= ~((xx > 7) & (yy > 8))
+    uh = (1.0 + 0.3 * np.sin(0.5 * yy) + 0.05 * rng.normal(size=shape)) * mh
+    vh = (0.2 * np.cos(0.4 * xx) + 0.05 * rng.normal(size=shape)) * mh
+    wh = (0.1 * np.sin(0.3 * zz + 0.2 * xx) + 0.05 * rng.normal(size=shape)) * mh
+    hh = (1.0, 1.5, 0.8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        uc, vc, wc = rp.clean_divergence_projection(uh, vh, wh, mh, *hh, iterations=3)
+        u1, v1, w1 = rp.clean_divergence_projection(uh, vh, wh, mh, *hh, iterations=1)
+    A, idx_map = rp.build_laplacian_matrix(mh, *hh)
+    xt = rng.normal(size=A.shape[0])
+    np.savez_compressed(os.path.join(OUT, "case_h_projection.npz"), u=uh, v=vh, w=wh, mask=mh, h=np.array(hh),
+                        u3=uc, v3=vc, w3=wc, u1=u1, v1=v1, w1=w1, lap_x=xt, lap_Ax=A @ xt,
+                        div0=rp.compute_consistent_divergence(uh, vh, wh, mh, *hh),
+                        div3=rp.compute_consistent_divergence(uc, vc, wc, mh, *hh))
     print("golden vectors written to", os.path.normpath(OUT))
 
 

@@ -26,6 +26,7 @@ __all__ = [
     "sibson_from_knn", "interpolate_field", "sample_mask_on_grid", "nearest_axis_index",
     "extract_boundary_particles", "compute_consistent_divergence", "flux_xy", "flux_xz",
     "flux_yz", "mid_plane_x_flux", "mean_abs_div", "apply_mask_zero", "outlier_keep_mask", "compute_strain_rate", "compute_vorticity",
+    "build_laplacian_matrix", "apply_consistent_correction", "clean_divergence_projection",
 ]
 
 
@@ -203,6 +204,85 @@ def apply_mask_zero(U, V, W, mask):
         a[~mask] = 0
         outs.append(a)
     return tuple(outs)
+
+
+# --------------------------------------------------------------------------- projection cleaning (N2)
+def build_laplacian_matrix(mask, dx, dy, dz):
+    """physics.py:55-108 -- masked 7-point Laplacian over fluid voxels as a CSR matrix + index map."""
+    from scipy import sparse
+    nz, ny, nx = mask.shape
+    n_fluid = np.sum(mask)
+    idx_map = np.full(mask.shape, -1, dtype=np.int32)
+    idx_map[mask] = np.arange(n_fluid)
+    rows, cols, data = [], [], []
+    I, J, K = np.where(mask)
+    curr = idx_map[I, J, K]
+    for axis, h2_inv in [(2, 1.0 / (dx**2)), (1, 1.0 / (dy**2)), (0, 1.0 / (dz**2))]:
+        for offset in [-1, 1]:
+            In, Jn, Kn = I, J, K
+            if axis == 2:
+                Kn = K + offset
+            elif axis == 1:
+                Jn = J + offset
+            else:
+                In = I + offset
+            valid_b = (In >= 0) & (In < nz) & (Jn >= 0) & (Jn < ny) & (Kn >= 0) & (Kn < nx)
+            neigh = np.full_like(curr, -1)
+            neigh[valid_b] = idx_map[In[valid_b], Jn[valid_b], Kn[valid_b]]
+            connected = neigh != -1
+            rows.append(curr[connected]); cols.append(neigh[connected])
+            data.append(np.full(np.sum(connected), h2_inv))
+            rows.append(curr[connected]); cols.append(curr[connected])
+            data.append(np.full(np.sum(connected), -h2_inv))
+    A = sparse.coo_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))),
+                          shape=(n_fluid, n_fluid))
+    return A.tocsr(), idx_map
+
+
+def apply_consistent_correction(u, v, w, phi, mask, dx, dy, dz):
+    """physics.py:110-147 -- subtract the cell average of the staggered face gradients of phi."""
+    phi_grid = np.zeros_like(u)
+    phi_grid[mask] = phi
+
+    def cell_grad(p, axis, m, h):
+        p = np.moveaxis(p, axis, -1)
+        m = np.moveaxis(m, axis, -1)
+        g_next = np.zeros_like(p)
+        g_next[..., :-1] = np.where(m[..., 1:] & m[..., :-1], (p[..., 1:] - p[..., :-1]) / h, 0.0)
+        g_prev = np.zeros_like(p)
+        g_prev[..., 1:] = g_next[..., :-1]
+        return np.moveaxis((g_next + g_prev) / 2.0, -1, axis)
+
+    u_new = u - cell_grad(phi_grid, 2, mask, dx)
+    v_new = v - cell_grad(phi_grid, 1, mask, dy)
+    w_new = w - cell_grad(phi_grid, 0, mask, dz)
+    u_new[~mask] = 0
+    v_new[~mask] = 0
+    w_new[~mask] = 0
+    return u_new, v_new, w_new
+
+
+def clean_divergence_projection(u, v, w, mask, dx, dy, dz, iterations=3, return_phi=False):
+    """physics.py:149-209 without the prints: divergence -> b - mean(b) -> lsqr(damp=1e-8,
+    atol=btol=1e-10, iter_lim=3000) -> correction, `iterations` times."""
+    from scipy.sparse.linalg import lsqr
+    u_c, v_c, w_c = u.copy(), v.copy(), w.copy()
+    phis = []
+    for i in range(iterations):
+        div = compute_consistent_divergence(u_c, v_c, w_c, mask, dx, dy, dz)
+        if i == 0:
+            A, _ = build_laplacian_matrix(mask, dx, dy, dz)
+        b = div[mask]
+        b = b - np.mean(b)
+        res = lsqr(A, b, damp=1e-8, atol=1e-10, btol=1e-10, iter_lim=3000, show=False)
+        phi = res[0]
+        phis.append(res)
+        if np.isnan(phi).any():
+            break
+        u_c, v_c, w_c = apply_consistent_correction(u_c, v_c, w_c, phi, mask, dx, dy, dz)
+    if return_phi:
+        return u_c, v_c, w_c, phis
+    return u_c, v_c, w_c
 
 
 # --------------------------------------------------------------------------- gradient stencils (N3)

@@ -23,7 +23,8 @@ EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
     "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_points", "ptv_outlier_filter",
     "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
-    "ptv_flux_profiles", "ptv_strain_vorticity", "ptv_interpolate_host",
+    "ptv_flux_profiles", "ptv_strain_vorticity", "ptv_poisson_workspace_bytes", "ptv_poisson_lsqr", "ptv_projection_correct",
+    "ptv_interpolate_host",
 ]
 
 
@@ -79,6 +80,13 @@ def _declare(lib):
     lib.ptv_flux_profiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.ptv_strain_vorticity.restype = i32
     lib.ptv_strain_vorticity.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, i32, vp, vp, vp]
+    lib.ptv_poisson_workspace_bytes.restype = i64
+    lib.ptv_poisson_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ptv_poisson_lsqr.restype = i32
+    lib.ptv_poisson_lsqr.argtypes = [vp, i32, vp, i32, i32, i32, f64, f64, f64, f64, f64, f64, f64, i32, vp, vp,
+                                     C.POINTER(f64 * 8), vp]
+    lib.ptv_projection_correct.restype = i32
+    lib.ptv_projection_correct.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, i32, vp, vp, vp, vp]
     lib.ptv_interpolate_host.restype = i32
     lib.ptv_interpolate_host.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp, i32, vp, i32, i32, f64, f64, i32,
                                          vp, vp, vp]

@@ -289,6 +289,38 @@ class PTVEngine:
                                                       self._stream()))
         return s, o
 
+    def poisson_lsqr(self, div, mask, dx, dy, dz, damp=1e-8, atol=1e-10, btol=1e-10, conlim=1e8, iter_lim=3000):
+        """LSQR solve of the masked Laplacian system for div - mean(div[mask]) (physics.py:180-186).
+        Returns (phi float64 (nz,ny,nx), info dict)."""
+        nz, ny, nx = div.shape
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        div, mask = div.contiguous(), mask.contiguous()
+        phi = torch.empty((nz, ny, nx), dtype=torch.float64, device=self.device)
+        nbytes = int(self.lib.ptv_poisson_workspace_bytes(nx, ny, nz))
+        work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+        info = (C.c_double * 8)()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_poisson_lsqr(_ptr(div), _dtype_code(div.dtype), _ptr(mask), nx, ny, nz, float(dx),
+                                                  float(dy), float(dz), float(damp), float(atol), float(btol),
+                                                  float(conlim), int(iter_lim), _ptr(phi), _ptr(work), C.byref(info),
+                                                  self._stream()))
+        keys = ("istop", "itn", "r1norm", "r2norm", "anorm", "acond", "arnorm", "xnorm")
+        return phi, {k: (int(v) if k in ("istop", "itn") else float(v)) for k, v in zip(keys, info)}
+
+    def projection_correct(self, u, v, w, phi, mask, dx, dy, dz):
+        """apply_consistent_correction (physics.py:110-147): returns the corrected (u, v, w)."""
+        nz, ny, nx = u.shape
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        u, v, w, mask, phi = u.contiguous(), v.contiguous(), w.contiguous(), mask.contiguous(), phi.contiguous()
+        out = torch.empty((3, nz, ny, nx), dtype=u.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_projection_correct(_ptr(u), _ptr(v), _ptr(w), _ptr(phi), _ptr(mask), nx, ny, nz,
+                                                        float(dx), float(dy), float(dz), _dtype_code(u.dtype),
+                                                        _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), self._stream()))
+        return out[0], out[1], out[2]
+
     def flux_profiles(self, u, v, w):
         """Unscaled plane sums (q_xy[nz], q_xz[ny], q_yz[nx]) as float64 CUDA tensors."""
         ref = next(t for t in (u, v, w) if t is not None)

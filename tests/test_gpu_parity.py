@@ -559,3 +559,43 @@ def test_strain_vorticity_golden(golden_dir):
     assert s32.dtype == np.float32 and np.array_equal(s32, ref.astype(np.float32))
     with pytest.raises(ValueError):
         gva.compute_vorticity(np.zeros((1, 4, 4)), np.zeros((1, 4, 4)), np.zeros((1, 4, 4)), 1, 1, 1)
+
+
+# ------------------------------------------------------------------ N2: projection cleaning
+def test_projection_cleaning_golden(golden_dir, capsys):
+    g = np.load(os.path.join(golden_dir, "case_h_projection.npz"))
+    dx, dy, dz = (float(h) for h in g["h"])
+    mask = g["mask"]
+    eng = PTVEngine()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    # the matrix-free Laplacian against the reference's CSR matrix, through one LSQR start-up: A^T b
+    # is what the first v vector is, so compare via the correction of a known potential instead
+    phi_grid = np.zeros(mask.shape)
+    phi_grid[mask] = g["lap_x"]
+    uc, vc, wc = eng.projection_correct(t(g["u"]), t(g["v"]), t(g["w"]), t(phi_grid), t(mask), dx, dy, dz)
+    ru, rv, rw = rp.apply_consistent_correction(g["u"], g["v"], g["w"], g["lap_x"], mask, dx, dy, dz)
+    for a, b in ((uc, ru), (vc, rv), (wc, rw)):
+        assert np.abs(a.cpu().numpy() - b).max() <= 1e-13
+    # one LSQR solve: same stopping reason and iteration count as SciPy, solution within 1e-8
+    from scipy.sparse.linalg import lsqr
+    A, _ = rp.build_laplacian_matrix(mask, dx, dy, dz)
+    b = g["div0"][mask]
+    b = b - b.mean()
+    ref = lsqr(A, b, damp=1e-8, atol=1e-10, btol=1e-10, iter_lim=3000)
+    phi, info = eng.poisson_lsqr(t(g["div0"]), t(mask), dx, dy, dz)
+    assert info["istop"] == ref[1] and abs(info["itn"] - ref[2]) <= 2, (info, ref[1:3])
+    scale = np.abs(ref[0]).max()
+    assert np.abs(phi.cpu().numpy()[mask] - ref[0]).max() <= 1e-7 * scale
+    assert np.all(phi.cpu().numpy()[~mask] == 0)
+    # anorm accumulates one term per iteration: an iteration count off by one moves it by ~1e-4
+    assert abs(info["anorm"] - ref[5]) <= 2e-3 * ref[5] and abs(info["xnorm"] - ref[8]) <= 1e-6 * ref[8]
+    # the whole driver (3 iterations) against the reference's output
+    u3, v3, w3 = gp.clean_divergence_projection(g["u"], g["v"], g["w"], mask, dx, dy, dz, iterations=3)
+    out = capsys.readouterr().out
+    assert "DIVERGENCE CLEANING COMPLETE" in out and "Net X-Flux" in out
+    for a, b in ((u3, g["u3"]), (v3, g["v3"]), (w3, g["w3"])):
+        assert a.dtype == np.float64 and np.abs(a - b).max() <= 1e-7
+    u1, v1, w1 = gp.clean_divergence(g["u"], g["v"], g["w"], mask, dx, dy, dz, iterations=1)
+    assert np.abs(u1 - g["u1"]).max() <= 1e-7 and np.abs(w1 - g["w1"]).max() <= 1e-7
+    with pytest.raises(NotImplementedError):
+        gp.clean_divergence(g["u"], g["v"], g["w"], mask, dx, dy, dz, method="variational")
