@@ -259,25 +259,42 @@ __global__ void __launch_bounds__(256) divergence_kernel(
 // then the shear-rate magnitude sqrt(0.5*(exx^2+eyy^2+ezz^2) + exy^2 + exz^2 + eyz^2) and |curl u|,
 // zeroed in solid voxels.  float64 arithmetic in NumPy's operation order (bit-identical for float64
 // fields).  HBM-bound: 13 B read + 4 B per output written per voxel.
-__device__ __forceinline__ double grad_div(double num, double den) {
-  if (num == 0.0) return den > 0.0 ? num : -num;  // signed zero without the division slow path
-  return __ddiv_rn(num, den);
+// num / den with the IEEE result.  When den is a power of two (unit spacing: 1 and 2) its reciprocal is
+// exact and the product is bit-identical to the quotient, so the division is skipped.
+struct Divisor {
+  double den, inv;
+  bool pow2;
+};
+__host__ __device__ inline Divisor make_divisor(double den) {
+  Divisor d;
+  d.den = den;
+  d.inv = 1.0 / den;
+  int e;
+  const double m = frexp(fabs(den), &e);
+  d.pow2 = (m == 0.5) && e > -1000 && e < 1000;
+  return d;
 }
+__device__ __forceinline__ double grad_div(double num, const Divisor& d) {
+  if (d.pow2) return __dmul_rn(num, d.inv);
+  if (num == 0.0) return d.den > 0.0 ? num : -num;  // signed zero without the division slow path
+  return __ddiv_rn(num, d.den);
+}
+
+struct Divisors6 { Divisor d[6]; };
 
 template <typename Tf>
 __device__ __forceinline__ double np_gradient(const Tf* __restrict__ f, int64_t i, int64_t stride, int pos, int n,
-                                              double h) {
-  if (n == 1) return 0.0;  // never reached: np.gradient needs >= 2 points (checked on the host)
-  if (pos == 0) return grad_div(__dsub_rn((double)f[i + stride], (double)f[i]), h);
-  if (pos == n - 1) return grad_div(__dsub_rn((double)f[i], (double)f[i - stride]), h);
-  return grad_div(__dsub_rn((double)f[i + stride], (double)f[i - stride]), __dmul_rn(2.0, h));
+                                              const Divisor& h1, const Divisor& h2) {
+  if (pos == 0) return grad_div(__dsub_rn((double)f[i + stride], (double)f[i]), h1);
+  if (pos == n - 1) return grad_div(__dsub_rn((double)f[i], (double)f[i - stride]), h1);
+  return grad_div(__dsub_rn((double)f[i + stride], (double)f[i - stride]), h2);
 }
 
 template <typename Tf>
 __global__ void __launch_bounds__(256) strain_vorticity_kernel(const Tf* __restrict__ u, const Tf* __restrict__ v,
                                                                 const Tf* __restrict__ w,
                                                                 const uint8_t* __restrict__ mask, int nx, int ny, int nz,
-                                                                double dx, double dy, double dz,
+                                                                const Divisors6 dv6,
                                                                 Tf* __restrict__ strain, Tf* __restrict__ vort) {
   const int64_t n = (int64_t)nx * ny * nz;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,12 +308,14 @@ __global__ void __launch_bounds__(256) strain_vorticity_kernel(const Tf* __restr
   const int y = (int)((i / nx) % ny);
   const int z = (int)(i / ((int64_t)nx * ny));
   const int64_t sy = nx, sz = (int64_t)nx * ny;
-  const double du_dx = np_gradient(u, i, 1, x, nx, dx), du_dy = np_gradient(u, i, sy, y, ny, dy),
-               du_dz = np_gradient(u, i, sz, z, nz, dz);
-  const double dv_dx = np_gradient(v, i, 1, x, nx, dx), dv_dy = np_gradient(v, i, sy, y, ny, dy),
-               dv_dz = np_gradient(v, i, sz, z, nz, dz);
-  const double dw_dx = np_gradient(w, i, 1, x, nx, dx), dw_dy = np_gradient(w, i, sy, y, ny, dy),
-               dw_dz = np_gradient(w, i, sz, z, nz, dz);
+  // edge spacing h and interior spacing 2h (np.gradient: (f[2:] - f[:-2]) / (2. * h))
+  const Divisor &x1 = dv6.d[0], &x2 = dv6.d[1], &y1 = dv6.d[2], &y2 = dv6.d[3], &z1 = dv6.d[4], &z2 = dv6.d[5];
+  const double du_dx = np_gradient(u, i, 1, x, nx, x1, x2), du_dy = np_gradient(u, i, sy, y, ny, y1, y2),
+               du_dz = np_gradient(u, i, sz, z, nz, z1, z2);
+  const double dv_dx = np_gradient(v, i, 1, x, nx, x1, x2), dv_dy = np_gradient(v, i, sy, y, ny, y1, y2),
+               dv_dz = np_gradient(v, i, sz, z, nz, z1, z2);
+  const double dw_dx = np_gradient(w, i, 1, x, nx, x1, x2), dw_dy = np_gradient(w, i, sy, y, ny, y1, y2),
+               dw_dz = np_gradient(w, i, sz, z, nz, z1, z2);
   if (strain) {
     const double exx = __dmul_rn(2.0, du_dx), eyy = __dmul_rn(2.0, dv_dy), ezz = __dmul_rn(2.0, dw_dz);
     const double exy = __dadd_rn(du_dy, dv_dx), exz = __dadd_rn(du_dz, dw_dx), eyz = __dadd_rn(dv_dz, dw_dy);
@@ -326,13 +345,17 @@ extern "C" int ptv_strain_vorticity(const void* d_u, const void* d_v, const void
   }
   const int64_t n = (int64_t)nx * ny * nz;
   const unsigned nb = (unsigned)((n + 255) / 256);
+  Divisors6 dv6;
+  dv6.d[0] = make_divisor(dx); dv6.d[1] = make_divisor(2.0 * dx);
+  dv6.d[2] = make_divisor(dy); dv6.d[3] = make_divisor(2.0 * dy);
+  dv6.d[4] = make_divisor(dz); dv6.d[5] = make_divisor(2.0 * dz);
   if (dtype == PTV_F32)
     strain_vorticity_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dx, dy, dz, (float*)d_strain,
+        (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dv6, (float*)d_strain,
         (float*)d_vorticity);
   else if (dtype == PTV_F64)
     strain_vorticity_kernel<double><<<nb, 256, 0, (cudaStream_t)stream>>>(
-        (const double*)d_u, (const double*)d_v, (const double*)d_w, d_mask, nx, ny, nz, dx, dy, dz, (double*)d_strain,
+        (const double*)d_u, (const double*)d_v, (const double*)d_w, d_mask, nx, ny, nz, dv6, (double*)d_strain,
         (double*)d_vorticity);
   else { set_error("ptv_strain_vorticity: bad dtype"); return PTV_ERR_INVALID; }
   count_launches(1);
