@@ -111,3 +111,28 @@ def test_synthetic_generators_small():
     assert 0.55 < float(c.float().mean()) < 0.68
     v = synthetic.cylinder_flow(p)
     assert v.shape == (1000, 3) and np.isfinite(v.numpy()).all()
+
+
+def test_compat_aliases_modules(tmp_path):
+    """compat.install(): the reference's import names resolve to the CUDA drop-ins, other names fall
+    through to the script directory's own modules."""
+    import importlib.util
+    import sys
+    from ptv_interpolation_b200 import compat
+    (tmp_path / "physics.py").write_text("def solve_poisson():\n    return 'reference'\n"
+                                         "def compute_consistent_divergence():\n    return 'reference'\n")
+    saved = {k: sys.modules.get(k) for k in ("interpolator", "physics", "filtering", "velocity_analysis")}
+    try:
+        compat.install(str(tmp_path))
+        import interpolator, physics, filtering  # noqa: E401
+        from ptv_interpolation_b200 import interpolator as gi2, physics as gp2
+        assert interpolator.interpolate_field is gi2.interpolate_field
+        assert physics.compute_consistent_divergence is gp2.compute_consistent_divergence
+        assert physics.solve_poisson() == "reference"
+        assert hasattr(filtering, "apply_filters")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
