@@ -599,3 +599,33 @@ def test_projection_cleaning_golden(golden_dir, capsys):
     assert np.abs(u1 - g["u1"]).max() <= 1e-7 and np.abs(w1 - g["w1"]).max() <= 1e-7
     with pytest.raises(NotImplementedError):
         gp.clean_divergence(g["u"], g["v"], g["w"], mask, dx, dy, dz, method="variational")
+
+
+def test_c1_config_vs_c_bruteforce_oracle():
+    """Config 1 (hex6 pack 128^3, 100k vectors, IDW k=50) against the SciPy-free C brute-force oracle on
+    15k random pore voxels: neighbour lists bit-exact (heap kernel), velocities of the streaming kernel
+    within the 1e-5 bar."""
+    from oracle.knn_brute import knn_brute
+    dev = torch.device("cuda", 0)
+    cfg, n, ax = _full_size_case("c1", dev)
+    eng = PTVEngine(dev)
+    mask = cfg["mask"].view(torch.uint8)
+    eng.build(cfg["points"], cfg["values"])
+    out = eng.interpolate(ax, ax, ax, mask=mask, method="idw", k=50, out_dtype=torch.float64)
+    assert eng.knn_stats()["used_stream"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(9)
+    lin = torch.nonzero(cfg["mask"].reshape(-1)).squeeze(1)
+    sel = lin[torch.randperm(lin.numel(), generator=g, device=dev)[:15000]]
+    zz, rem = sel // (n * n), sel % (n * n)
+    q = torch.stack([rem % n, rem // n, zz], -1).to(torch.float64)
+    pts, vals = cfg["points"].cpu().numpy(), cfg["values"].cpu().numpy()
+    d, i, _ = knn_brute(pts, q.cpu().numpy(), 50)
+    ref = rp.idw_from_knn(d, i, vals).T
+    got = out.reshape(3, -1)[:, sel].cpu().numpy()
+    _assert_vel(got[:, None, None, :], ref[:, None, None, :], vals)
+    # the same voxels as arbitrary query points through the heap kernel: lists bit-exact
+    qe = PTVEngine(dev)
+    qe.build(q, q)
+    _, kd, ki = eng.interpolate_points(qe, method="idw", k=50, return_knn=True)
+    assert np.array_equal(ki.cpu().numpy(), i) and np.array_equal(kd.cpu().numpy(), d)

@@ -148,3 +148,23 @@ def test_projection_cleaning_port(golden_dir):
     m0 = rp.mean_abs_div(g["div0"], g["mask"])
     m3 = rp.mean_abs_div(g["div3"], g["mask"])
     assert m3 < 0.6 * m0  # the cleaning does reduce the divergence
+
+
+def test_c_bruteforce_agrees_with_ckdtree_canonical(golden_dir):
+    """oracle/knn_brute.c (no SciPy, no NumPy arithmetic) against the cKDTree-based canonical search on a
+    random cloud and on the tie-heavy lattice case."""
+    from oracle.knn_brute import knn_brute
+    rng = np.random.default_rng(12)
+    pts = rng.uniform(0, 30, size=(20000, 3)).astype(np.float32).astype(np.float64)
+    q = rng.uniform(-2, 32, size=(3000, 3))
+    d, i, d2 = rp.knn_canonical(pts, q, 50, workers=-1)
+    db, ib, d2b = knn_brute(pts, q, 50)
+    assert np.array_equal(ib, i) and np.array_equal(d2b, d2) and np.array_equal(db, d)
+    g = _load(golden_dir, "case_b_boundary.npz")
+    grid, _ = rp.create_grid(((0, 12), (0, 12), (0, 12)), 12)
+    fc = rp.flat_coords(grid)
+    d, i, d2 = rp.knn_canonical(g["points"], fc, 20)
+    db, ib, _ = knn_brute(g["points"], fc, 20)
+    assert np.array_equal(ib, i) and np.array_equal(db, d)
+    with pytest.raises(IndexError):
+        knn_brute(pts[:5], q, 6)
