@@ -23,8 +23,8 @@
 
 namespace ptv {
 
-static constexpr int kNB = 48;        // histogram bins over [0, Tmax)
-static constexpr int kListCap = 20;   // capacity of the crossing-bin list
+static constexpr int kNB = 96;        // histogram bins over [0, Tmax), 16-bit counters
+static constexpr int kListCap = 16;   // capacity of the crossing-bin list
 static constexpr int kMinEstimate = 16;
 static_assert(kPipeCap == 128, "the exact passes use two 64-bit accept masks per chunk");
 
@@ -47,15 +47,16 @@ template <> struct StageVal<double> {
 };
 
 template <int T, int TX, int TY, int TZ, typename OutT>
-__global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
+__global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const KnnParams p) {
   static_assert(TX * TY * TZ == T, "tile shape");
   constexpr int NW = T / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // per-thread columns: histogram (phase A) aliases the crossing-bin list (phase B)
   double* lkey_all = reinterpret_cast<double*>(smem_raw);                       // [kListCap][T]
   int* lidx_all = reinterpret_cast<int*>(lkey_all + (size_t)kListCap * T);      // [kListCap][T]
-  int* hist_all = reinterpret_cast<int*>(smem_raw);                             // [kNB][T] (alias)
-  static_assert(kNB * 4 <= kListCap * 12, "histogram must fit under the list");
+  // 16-bit counters, bins 2j and 2j+1 of a thread share one 32-bit word: [kNB/2][T][2] (alias)
+  uint16_t* hist_all = reinterpret_cast<uint16_t*>(smem_raw);
+  static_assert(kNB * 2 <= kListCap * 12 && kNB % 2 == 0, "histogram must fit under the list");
   using ValT = typename StageVal<OutT>::type;  // float4 for float32 output, Value4 for float64 output
   constexpr int kVal = StageVal<OutT>::kind;
   ParticleRec* s64 = reinterpret_cast<ParticleRec*>(lidx_all + (size_t)kListCap * T);  // [2][kPipeCap]
@@ -152,15 +153,16 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     push_fail(1);
     return;
   }
-  // three scan radii whose squares sit just above histogram bin edges 18, 30 and 48 (= Tmax)
-  const double binw = p.rscale * r_est * r_est / 18.0;
+  // three scan radii whose squares sit just above histogram bin edges 36, 60 and 96 (= Tmax)
+  const double binw = p.rscale * r_est * r_est / 36.0;
   const float inv_w = (float)(1.0 / binw);
-  constexpr int kEdges[3] = {18, 30, kNB};
+  constexpr int kEdges[3] = {36, 60, kNB};
 
   // ---- phase A: grow the scanned region, float32 histogram of squared distances
-  int* hist = hist_all + t;
+  uint16_t* hist = hist_all + 2 * t;  // bin b at hist[(b >> 1) * 2 * T + (b & 1)]
+  unsigned* hist2 = reinterpret_cast<unsigned*>(hist);  // bin pair j at hist2[j * T]
 #pragma unroll
-  for (int b = 0; b < kNB; ++b) hist[b * T] = 0;
+  for (int j = 0; j < kNB / 2; ++j) hist2[j * T] = 0u;
   RoundRegion prev = make_region(g, tg, 0.0);
   RoundRegion rg = prev;
   bool have_prev = false, finished = false;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
           const float dx = qfx - c.x, dy = qfy - c.y, dz = qfz - c.z;
           const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
           const int b = min(kNB - 1, __float2int_rz(d2 * inv_w));
-          hist[b * T] += 1;
+          hist[(b >> 1) * 2 * T + (b & 1)] += 1;
         }
       }
     });
@@ -189,7 +191,10 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
     if (active && !last) {
       int cum = 0;
       const int nfull = min(kEdges[stage], kNB - 1);
-      for (int b = 0; b < nfull; ++b) cum += hist[b * T];
+      for (int j = 0; j < nfull / 2; ++j) {  // kEdges are even: whole pairs
+        const unsigned pr = hist2[j * T];
+        cum += (int)(pr & 0xffffu) + (int)(pr >> 16);
+      }
       done = cum >= k;
     }
     if (__syncthreads_and(done ? 1 : 0) || last) {
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(T) knn_stream_kernel(const KnnParams p) {
   if (active) {
     int cum = 0, bstar = -1;
     for (int b = 0; b < kNB - 1; ++b) {
-      const int h = hist[b * T];
+      const int h = hist[(b >> 1) * 2 * T + (b & 1)];
       if (cum + h >= k) {
         bstar = b;
         if (h > kListCap) fail = true;
