@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   // per-thread columns: histogram (phase A) aliases the crossing-bin list (phase B)
   double* lkey_all = reinterpret_cast<double*>(smem_raw);                       // [kListCap][T]
   int* lidx_all = reinterpret_cast<int*>(lkey_all + (size_t)kListCap * T);      // [kListCap][T]
-  // 16-bit counters, bins 2j and 2j+1 of a thread share one 32-bit word: [kNB/2][T][2] (alias)
+  // 16-bit counters [kNB][T] (alias): two lanes share a 32-bit word, which is conflict-free
   uint16_t* hist_all = reinterpret_cast<uint16_t*>(smem_raw);
   static_assert(kNB * 2 <= kListCap * 12 && kNB % 2 == 0, "histogram must fit under the list");
   using ValT = typename StageVal<OutT>::type;  // float4 for float32 output, Value4 for float64 output
@@ -159,10 +159,9 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   constexpr int kEdges[3] = {36, 60, kNB};
 
   // ---- phase A: grow the scanned region, float32 histogram of squared distances
-  uint16_t* hist = hist_all + 2 * t;  // bin b at hist[(b >> 1) * 2 * T + (b & 1)]
-  unsigned* hist2 = reinterpret_cast<unsigned*>(hist);  // bin pair j at hist2[j * T]
+  uint16_t* hist = hist_all + t;
 #pragma unroll
-  for (int j = 0; j < kNB / 2; ++j) hist2[j * T] = 0u;
+  for (int b = 0; b < kNB; ++b) hist[b * T] = 0;
   RoundRegion prev = make_region(g, tg, 0.0);
   RoundRegion rg = prev;
   bool have_prev = false, finished = false;
@@ -181,7 +180,7 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
           const float dx = qfx - c.x, dy = qfy - c.y, dz = qfz - c.z;
           const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
           const int b = min(kNB - 1, __float2int_rz(d2 * inv_w));
-          hist[(b >> 1) * 2 * T + (b & 1)] += 1;
+          hist[b * T] += 1;
         }
       }
     });
@@ -191,10 +190,7 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
     if (active && !last) {
       int cum = 0;
       const int nfull = min(kEdges[stage], kNB - 1);
-      for (int j = 0; j < nfull / 2; ++j) {  // kEdges are even: whole pairs
-        const unsigned pr = hist2[j * T];
-        cum += (int)(pr & 0xffffu) + (int)(pr >> 16);
-      }
+      for (int b = 0; b < nfull; ++b) cum += hist[b * T];
       done = cum >= k;
     }
     if (__syncthreads_and(done ? 1 : 0) || last) {
@@ -216,7 +212,7 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   if (active) {
     int cum = 0, bstar = -1;
     for (int b = 0; b < kNB - 1; ++b) {
-      const int h = hist[(b >> 1) * 2 * T + (b & 1)];
+      const int h = hist[b * T];
       if (cum + h >= k) {
         bstar = b;
         if (h > kListCap) fail = true;
