@@ -59,4 +59,20 @@ out["N2_lsqr_512"] = {"fluid_voxels": int(m2.sum()), "iterations": info["itn"], 
                       "GBps": (2 * 25.0 + 40.0) * n2**3 * info["itn"] / dt / 1e9}
 ms, _ = timed(lambda: eng.projection_correct(div, div, div, phi, m2, 1.0, 1.0, 1.0))
 out["N2_correction_512"] = {"ms": ms, "GBps": (12 + 8 + 1 + 12) * n2**3 / ms / 1e6}
+# a2 / a3: mask resampling gather (2 B/voxel) and boundary-voxel extraction at 1024^3
+del div, phi, m2
+n = 1024
+mraw = synthetic.fcc_sphere_pack_mask(n, device=dev).view(torch.uint8)
+ident = torch.arange(n, device=dev, dtype=torch.int32)
+ms, _ = timed(lambda: eng.mask_gather(mraw, ident, ident, ident))
+out["a2_mask_gather_1024"] = {"ms": ms, "GBps": 2.0 * n**3 / ms / 1e6, "frac_of_measured_peak": 2.0 * n**3 / ms / 1e6 / PEAK}
+half = torch.arange(0, n, 2, device=dev, dtype=torch.int32)
+ms, _ = timed(lambda: eng.mask_gather(mraw, half, half, half))
+out["a2_mask_gather_1024_to_512"] = {"ms": ms}
+for th in (1, 2):
+    t0 = time.perf_counter()
+    idx = eng.boundary_voxels(mraw, thickness=th)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out[f"a3_boundary_voxels_1024_t{th}"] = {"ms_wall": dt * 1e3, "count": int(idx.numel())}
 print(json.dumps(out))
