@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   const int rounds = (nact + T - 1) / T;
   int round_start = 0;
   for (int round = 0; round < rounds; ++round) {
-  const int round_cnt = nact / rounds + (round < nact % rounds ? 1 : 0);
+  // greedy rounds: full warps first -- a short last round leaves whole warps idle at the barriers, which
+  // costs no issue slots, instead of spreading idle lanes over every warp of every round
+  const int round_cnt = min(T, nact - round_start);
   const bool active = t < round_cnt;
   const bool valid = active;
   int ix = 0, iy = 0, iz = 0;
