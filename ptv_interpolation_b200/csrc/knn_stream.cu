@@ -26,6 +26,7 @@ namespace ptv {
 static constexpr int kNB = 96;        // histogram bins over [0, Tmax), 16-bit counters
 static constexpr int kListCap = 16;   // capacity of the crossing-bin list
 static constexpr int kMinEstimate = 16;
+static constexpr int kVPT = 8;  // voxels of the region examined per thread (region = kVPT * T voxels)
 static_assert(kPipeCap == 128, "the exact passes use two 64-bit accept masks per chunk");
 
 // Values staged next to the candidates: float32 when the output is float32 (rounding 6e-8 relative,
@@ -67,16 +68,16 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   int* seg_off = seg_start + T;
   int* warp_tot = seg_off + T + 1;
   const PipeBuf pbuf[2] = {{s64, s32, sval}, {s64 + kPipeCap, s32 + kPipeCap, sval + kPipeCap}};
-  uint16_t* vlist = reinterpret_cast<uint16_t*>(warp_tot + NW + 1);  // [4*T] compacted active voxels
+  uint16_t* vlist = reinterpret_cast<uint16_t*>(warp_tot + NW + 1);  // [kVPT*T] compacted active voxels
 
   const int t = threadIdx.x;
   const int k = p.k;
   const HashGrid& g = p.g;
-  // ---- region of 4*T voxels (4x4x4 blocks, block-major) -> compact list of its ACTIVE voxels, so
+  // ---- region of kVPT*T voxels (4x4x4 blocks, block-major) -> compact list of its ACTIVE voxels, so
   //      that every lane of a round owns a pore voxel even where the tile straddles a grain surface
-  constexpr int RX = 8, RY = T >= 64 ? 8 : 4, RZ = T == 128 ? 8 : 4;
+  constexpr int RX = 8, RY = T >= 64 ? 8 : 4, RZ = (T == 128 ? 8 : 4) * (kVPT / 4);
   constexpr int NBX = RX / 4, NBY = RY / 4;
-  static_assert(RX * RY * RZ == 4 * T, "region holds four voxels per thread");
+  static_assert(RX * RY * RZ == kVPT * T && kVPT % 4 == 0, "region holds kVPT voxels per thread");
   const int region = blockIdx.x;
   const int rx = region % p.tiles_x;
   const int ry = (region / p.tiles_x) % p.tiles_y;
@@ -105,9 +106,9 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
     int mine = 0;
     unsigned flags = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < kVPT; ++q) {
       int ix, iy, iz;
-      decode(4 * t + q, ix, iy, iz);
+      decode(kVPT * t + q, ix, iy, iz);
       if (ix < p.nx && iy < p.ny && iz < p.nz) {
         const int64_t vox = ((int64_t)iz * p.ny + iy) * p.nx + ix;
         if (p.mask == nullptr || p.mask[vox] != 0) {
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
     const int off = block_scan_excl<T>(mine, warp_tot, &nact);
     int o = off;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (flags & (1u << q)) vlist[o++] = (uint16_t)(4 * t + q);
+    for (int q = 0; q < kVPT; ++q)
+      if (flags & (1u << q)) vlist[o++] = (uint16_t)(kVPT * t + q);
   }
   if (nact == 0) return;
   __syncthreads();
@@ -415,13 +416,13 @@ static size_t stream_smem_bytes(int T, bool f32) {
   const int NW = T / 32;
   size_t b = (size_t)kListCap * T * 12 +
              (size_t)2 * kPipeCap * (sizeof(ParticleRec) + sizeof(float4) + (f32 ? sizeof(float4) : sizeof(Value4))) +
-             (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 2 + NW) * sizeof(int) + (size_t)4 * T * sizeof(uint16_t);
+             (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 2 + NW) * sizeof(int) + (size_t)kVPT * T * sizeof(uint16_t);
   return (b + 15) & ~(size_t)15;
 }
 
 template <int T, int TX, int TY, int TZ, typename OutT>
 static int launch_stream_t(KnnParams& p, cudaStream_t stream) {
-  constexpr int RX = 8, RY = T >= 64 ? 8 : 4, RZ = T == 128 ? 8 : 4;  // region = four voxels per thread
+  constexpr int RX = 8, RY = T >= 64 ? 8 : 4, RZ = (T == 128 ? 8 : 4) * (kVPT / 4);  // region = kVPT voxels per thread
   p.tiles_x = (p.nx + RX - 1) / RX;
   p.tiles_y = (p.ny + RY - 1) / RY;
   p.tiles_z = (p.nz + RZ - 1) / RZ;
