@@ -38,7 +38,7 @@ void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 struct Tuning {
-  double ppc = 1.0;  // target particles per cell
+  double ppc = 0.5;  // target particles per cell (finer cells -> tighter scan regions)
   int r0 = 1;        // rings merged into the first staging batch
   int tile = 128;    // threads (= voxels) per tile, heap kernel
   int stream = 1;    // 1 = streaming kernel for idw/sibson with k >= 8 (heap kernel as fallback)

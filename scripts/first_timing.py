@@ -21,7 +21,7 @@ def main():
         ax = torch.linspace(0, n - 1, n, dtype=torch.float64, device=dev)
         pore = int(cfg["mask"].sum())
         for var in variants:
-            set_tuning(tile=128, r0=1, ppc=1.0, stream=1, stream_tile=128, stats=0, rscale=1.3)
+            set_tuning(tile=128, r0=1, ppc=0.5, stream=1, stream_tile=128, stats=0, rscale=1.3)
             set_tuning(**var)
             for masked in (True, False):
                 if not masked and n > 512:

@@ -216,7 +216,7 @@ def test_tuning_does_not_change_neighbours(case_a, tune):
         set_tuning(**tune)
         U, V, W, kd, ki = gi.interpolate_field(df, grid, method="idw", idw_neighbors=50, return_knn=True)
     finally:
-        set_tuning(tile=128, r0=1, ppc=1.0)
+        set_tuning(tile=128, r0=1, ppc=0.5)
     assert np.array_equal(ki, g["knn_i_k50"]) and np.array_equal(kd, g["knn_d_k50"])
 
 
@@ -249,7 +249,7 @@ def test_stream_kernel_matches_heap_kernel(case_a, tune, kw):
         set_tuning(**tune)
         _stream_vs_heap(df, grid, **kw)
     finally:
-        set_tuning(stream_tile=128, r0=1, ppc=1.0)
+        set_tuning(stream_tile=128, r0=1, ppc=0.5)
 
 
 def test_stream_kernel_sphere_pack_and_fallback_paths():
