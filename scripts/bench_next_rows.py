@@ -29,6 +29,18 @@ def timed(fn, reps=3):
     return best, r
 
 
+# a7 / a8: sibson (c3: 512^3, 5M vectors, k=50) and local RBF (c2: 256^3, 1M vectors, k=20) on pore voxels
+for name, method, k in (("c3", "sibson", 50), ("c2", "rbf", 20), ("c2", "nearest", 1)):
+    cfg = synthetic.make_config(name, device=dev)
+    nn = cfg["n"]
+    axx = torch.linspace(0, nn - 1, nn, dtype=torch.float64, device=dev)
+    mm = cfg["mask"].view(torch.uint8)
+    eng.build(cfg["points"], cfg["values"])
+    ms, _ = timed(lambda: eng.interpolate(axx, axx, axx, mask=mm, method=method, k=k), reps=2)
+    pore = int(cfg["mask"].sum())
+    out[f"{method}_{name}"] = {"k": k, "grid": nn, "ms": ms, "pore_voxels_per_s": pore / ms * 1e3}
+    del cfg, mm
+
 # N1: outlier filter, 10M particles of the c4 cloud, k = 25
 cfg = synthetic.make_config("c4", device=dev)
 eng.build(cfg["points"], cfg["values"])
