@@ -329,6 +329,100 @@ __global__ void __launch_bounds__(256) strain_vorticity_kernel(const Tf* __restr
   }
 }
 
+// Vectorised variant (nx % 4 == 0, 16-byte aligned rows): one thread = 4 consecutive x; every field
+// contributes 5 vector loads (centre, y-1, y+1, z-1, z+1) and 2 scalar x-halo loads per 4 voxels instead
+// of 28 scalar loads.  Same arithmetic, same operation order.
+template <typename Tf>
+__device__ __forceinline__ void ld4(const Tf* __restrict__ p, double (&o)[4]) {
+  if (sizeof(Tf) == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+}
+
+template <typename Tf>
+struct Grad4 { double dx[4], dy[4], dz[4]; };
+
+template <typename Tf>
+__device__ __forceinline__ Grad4<Tf> gradients4(const Tf* __restrict__ f, int64_t i, int x, int y, int z, int nx, int ny,
+                                                int nz, const Divisors6& dv) {
+  const int64_t sy = nx, sz = (int64_t)nx * ny;
+  double e[6], c[4], a[4], b[4];
+  ld4(f + i, c);
+  e[0] = x > 0 ? (double)f[i - 1] : 0.0;
+  e[5] = x + 4 < nx ? (double)f[i + 4] : 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e[j + 1] = c[j];
+  Grad4<Tf> g;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pos = x + j;
+    if (pos == 0) g.dx[j] = grad_div(__dsub_rn(e[j + 2], e[j + 1]), dv.d[0]);
+    else if (pos == nx - 1) g.dx[j] = grad_div(__dsub_rn(e[j + 1], e[j]), dv.d[0]);
+    else g.dx[j] = grad_div(__dsub_rn(e[j + 2], e[j]), dv.d[1]);
+  }
+  if (y == 0) { ld4(f + i + sy, b); for (int j = 0; j < 4; ++j) g.dy[j] = grad_div(__dsub_rn(b[j], c[j]), dv.d[2]); }
+  else if (y == ny - 1) { ld4(f + i - sy, a); for (int j = 0; j < 4; ++j) g.dy[j] = grad_div(__dsub_rn(c[j], a[j]), dv.d[2]); }
+  else { ld4(f + i - sy, a); ld4(f + i + sy, b); for (int j = 0; j < 4; ++j) g.dy[j] = grad_div(__dsub_rn(b[j], a[j]), dv.d[3]); }
+  if (z == 0) { ld4(f + i + sz, b); for (int j = 0; j < 4; ++j) g.dz[j] = grad_div(__dsub_rn(b[j], c[j]), dv.d[4]); }
+  else if (z == nz - 1) { ld4(f + i - sz, a); for (int j = 0; j < 4; ++j) g.dz[j] = grad_div(__dsub_rn(c[j], a[j]), dv.d[4]); }
+  else { ld4(f + i - sz, a); ld4(f + i + sz, b); for (int j = 0; j < 4; ++j) g.dz[j] = grad_div(__dsub_rn(b[j], a[j]), dv.d[5]); }
+  return g;
+}
+
+template <typename Tf>
+__global__ void __launch_bounds__(256) strain_vorticity_vec4_kernel(const Tf* __restrict__ u, const Tf* __restrict__ v,
+                                                                     const Tf* __restrict__ w,
+                                                                     const uint8_t* __restrict__ mask, int nx, int ny,
+                                                                     int nz, const Divisors6 dv6, Tf* __restrict__ strain,
+                                                                     Tf* __restrict__ vort) {
+  const int gx = nx >> 2;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)gx * ny * nz) return;
+  const int x = (int)(gid % gx) * 4;
+  const int64_t row = gid / gx;
+  const int y = (int)(row % ny), z = (int)(row / ny);
+  const int64_t i = row * nx + x;
+  uchar4 m = make_uchar4(1, 1, 1, 1);
+  if (mask != nullptr) m = *reinterpret_cast<const uchar4*>(mask + i);
+  const bool mk[4] = {m.x != 0, m.y != 0, m.z != 0, m.w != 0};
+  double so[4] = {0.0, 0.0, 0.0, 0.0}, vo[4] = {0.0, 0.0, 0.0, 0.0};
+  if (mk[0] || mk[1] || mk[2] || mk[3]) {
+    const Grad4<Tf> gu = gradients4(u, i, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gv = gradients4(v, i, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gw = gradients4(w, i, x, y, z, nx, ny, nz, dv6);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!mk[j]) continue;
+      if (strain) {
+        const double exx = __dmul_rn(2.0, gu.dx[j]), eyy = __dmul_rn(2.0, gv.dy[j]), ezz = __dmul_rn(2.0, gw.dz[j]);
+        const double exy = __dadd_rn(gu.dy[j], gv.dx[j]), exz = __dadd_rn(gu.dz[j], gw.dx[j]),
+                     eyz = __dadd_rn(gv.dz[j], gw.dy[j]);
+        const double diag = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(exx, exx), __dmul_rn(eyy, eyy)), __dmul_rn(ezz, ezz)));
+        so[j] = sqrt(__dadd_rn(__dadd_rn(__dadd_rn(diag, __dmul_rn(exy, exy)), __dmul_rn(exz, exz)), __dmul_rn(eyz, eyz)));
+      }
+      if (vort) {
+        const double vx = __dsub_rn(gw.dy[j], gv.dz[j]), vy = __dsub_rn(gu.dz[j], gw.dx[j]), vz = __dsub_rn(gv.dx[j], gu.dy[j]);
+        vo[j] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+      }
+    }
+  }
+  auto st4 = [&](Tf* p, const double (&d)[4]) {
+    if (sizeof(Tf) == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
+    } else {
+      *reinterpret_cast<double2*>(p) = make_double2(d[0], d[1]);
+      *(reinterpret_cast<double2*>(p) + 1) = make_double2(d[2], d[3]);
+    }
+  };
+  if (strain) st4(strain + i, so);
+  if (vort) st4(vort + i, vo);
+}
+
 }  // namespace ptv
 
 using namespace ptv;
@@ -349,7 +443,19 @@ extern "C" int ptv_strain_vorticity(const void* d_u, const void* d_v, const void
   dv6.d[0] = make_divisor(dx); dv6.d[1] = make_divisor(2.0 * dx);
   dv6.d[2] = make_divisor(dy); dv6.d[3] = make_divisor(2.0 * dy);
   dv6.d[4] = make_divisor(dz); dv6.d[5] = make_divisor(2.0 * dz);
-  if (dtype == PTV_F32)
+  const auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = (nx % 4 == 0) && al16(d_u) && al16(d_v) && al16(d_w) && al16(d_strain) && al16(d_vorticity) &&
+                   (d_mask == nullptr || (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0);
+  const unsigned nbv = (unsigned)((n / 4 + 255) / 256);
+  if (vec && dtype == PTV_F32)
+    strain_vorticity_vec4_kernel<float><<<nbv, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dv6, (float*)d_strain,
+        (float*)d_vorticity);
+  else if (vec && dtype == PTV_F64)
+    strain_vorticity_vec4_kernel<double><<<nbv, 256, 0, (cudaStream_t)stream>>>(
+        (const double*)d_u, (const double*)d_v, (const double*)d_w, d_mask, nx, ny, nz, dv6, (double*)d_strain,
+        (double*)d_vorticity);
+  else if (dtype == PTV_F32)
     strain_vorticity_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(
         (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dv6, (float*)d_strain,
         (float*)d_vorticity);

@@ -559,6 +559,17 @@ def test_strain_vorticity_golden(golden_dir):
     assert s32.dtype == np.float32 and np.array_equal(s32, ref.astype(np.float32))
     with pytest.raises(ValueError):
         gva.compute_vorticity(np.zeros((1, 4, 4)), np.zeros((1, 4, 4)), np.zeros((1, 4, 4)), 1, 1, 1)
+    # vectorised path (nx % 4 == 0): unit and non-unit spacing, with and without mask, both dtypes
+    rng = np.random.default_rng(4)
+    for shape, h in (((6, 7, 16), (1.0, 1.0, 1.0)), ((5, 2, 8), (0.7, 2.0, 1.3)), ((2, 9, 4), (2.0, 0.5, 4.0))):
+        u, v, w = (rng.normal(size=shape) for _ in range(3))
+        m = rng.random(shape) > 0.3
+        for mm in (None, m):
+            assert np.array_equal(gva.compute_strain_rate(u, v, w, *h, mask=mm), rp.compute_strain_rate(u, v, w, *h, mask=mm))
+            assert np.array_equal(gva.compute_vorticity(u, v, w, *h, mask=mm), rp.compute_vorticity(u, v, w, *h, mask=mm))
+        uf, vf, wf = (a.astype(np.float32) for a in (u, v, w))
+        ref = rp.compute_vorticity(uf.astype(np.float64), vf.astype(np.float64), wf.astype(np.float64), *h, mask=m)
+        assert np.array_equal(gva.compute_vorticity(uf, vf, wf, *h, mask=m), ref.astype(np.float32))
 
 
 # ------------------------------------------------------------------ N2: projection cleaning
