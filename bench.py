@@ -361,7 +361,7 @@ def run_b200(args):
                 "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full
                 # capture of this workload (profiles/r01_v3_knn_stream_c4_ncu_full.csv); null for other workloads
-                "traffic": 21.54e9 if (args.workload == "c4" and world == 1 and used_stream) else None,
+                "traffic": 20.78e9 if (args.workload == "c4" and world == 1 and used_stream) else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": knn_ms,
                 "note": "kNN selection is SM-issue bound, not HBM bound (DESIGN.md); the HBM-bound kernels are "

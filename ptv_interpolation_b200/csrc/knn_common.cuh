@@ -392,8 +392,8 @@ __device__ __forceinline__ double estimate_radius(const HashGrid& g, const TileG
       const double vol = (double)(b1[0] - b0[0] + 1) * nry * (b1[2] - b0[2] + 1) * g.cell * g.cell * g.cell;
       return cbrt(0.238732414637843 * k * vol / n1);  // (3k / (4 pi rho))^(1/3)
     }
-    if (attempt >= 3 || whole) return -1.0;
-    r += 1;
+    if (attempt >= 10 || whole) return -1.0;
+    r += attempt < 3 ? 1 : (r + 1) / 2;  // 1, 2, 3, 4, 6, 9, 14, ... cells: voids (e.g. voxels inside grains)
   }
 }
 

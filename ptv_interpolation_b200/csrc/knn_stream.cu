@@ -1,24 +1,28 @@
 // Streaming (heap-free) fused kNN + IDW / sibson kernel -- the production path for k >= 8.
 //
-// Same mapping as the heap kernel (one CTA = one voxel tile, one thread = one voxel, cell-list
-// rings staged through shared memory), but the per-voxel k-best list is never materialised:
+// One CTA owns an 8x8x16 region of voxels, compacts its ACTIVE (pore) voxels and processes them in
+// rounds of up to 128 lanes (one thread = one voxel).  Per round the cell list around the round's
+// bounding box is scanned through shared memory (knn_common.cuh: rounded regions, cp.async double
+// buffering), but the per-voxel k-best list is never materialised:
 //
-//   phase A  walk the rings; every thread histograms the float32 squared distances of the staged
-//            particles into 32 bins (bin width from the tile's local particle density).  Stop when
-//            every voxel has >= k particles closer than the scanned box's nearest face (exact
-//            criterion, conservative in float32).  The bin where the cumulative count crosses k
-//            gives two float64 thresholds E_lo < E_hi per voxel.
-//   phase B  rescan the final box.  A float32 pre-test rejects far particles; the rest get the exact
-//            float64 key d2 = (dx*dx + dy*dy) + dz*dz.  Keys below E_lo are certainly among the k
-//            nearest and are accumulated on the fly; keys in [E_lo, E_hi) go to a short list
-//            (<= 20 entries) from which the k - n_in smallest by (d2, index) are taken.
+//   phase A  grow the scanned region through three radii; every thread histograms the float32 squared
+//            distances of the staged particles into 96 16-bit bins (bin width from the tile's local
+//            particle density).  Stop when every voxel has >= k particles in bins that lie wholly inside
+//            the scanned radius.  The bin where the cumulative count crosses k gives two float64
+//            thresholds E_lo < E_hi per voxel.
+//   phase B  rescan the final region.  A float32 pre-test builds per-lane accept masks; accepted
+//            particles get the exact float64 key d2 = (dx*dx + dy*dy) + dz*dz.  Keys below E_lo are
+//            certainly among the k nearest and are accumulated on the fly; keys in [E_lo, E_hi) go to a
+//            short list (<= 16 entries) from which the k - n_in smallest by (d2, index) are taken.
 //   phase C  (sibson only) one more rescan to apply weights that need the std of the k distances.
 //
-// The selected SET is exactly the canonical k nearest whenever n_in <= k <= n_in + n_list; any tile
-// where that cannot be established (histogram overflow, list overflow, too few particles near the
-// tile) is appended to a fail list and redone by the exact heap kernel (knn_interp.cu), so results
-// never depend on the optimistic path succeeding.  Shared memory per thread drops from 12*k bytes
-// to 240 bytes (5 CTAs/SM instead of 2 at k = 50) and the divergent heap maintenance disappears.
+// The selected SET is exactly the canonical k nearest whenever n_in <= k <= n_in + n_list and every key
+// below E_hi was scanned (E_hi <= scanned radius^2 by construction).  Any region where that cannot be
+// established (no local density estimate, k-th neighbour beyond the histogram range, crossing bin
+// larger than the list, verification failure) is appended to a fail list and redone by the exact heap
+// kernel (knn_interp.cu), so results never depend on the optimistic path succeeding.  Shared memory
+// per voxel drops from 12*k bytes to 192 bytes (5 CTAs/SM instead of 2 at k = 50), the divergent heap
+// maintenance disappears, and the main loops run in float32.
 #include "knn_common.cuh"
 
 namespace ptv {
@@ -136,7 +140,6 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   // costs no issue slots, instead of spreading idle lanes over every warp of every round
   const int round_cnt = min(T, nact - round_start);
   const bool active = t < round_cnt;
-  const bool valid = active;
   int ix = 0, iy = 0, iz = 0;
   if (active) decode(vlist[round_start + t], ix, iy, iz);
   round_start += round_cnt;
