@@ -311,8 +311,14 @@ def run_b200(args):
         dp, dv, dm, dax = (torch.empty_like(t, device=dev) for t in (hp, hv, hm, hax))
 
         def e2e_step():
-            dp.copy_(hp, non_blocking=True)
-            dv.copy_(hv, non_blocking=True)
+            # the particle table enters the box once (rank 0, pinned host -> HBM) and is replicated over
+            # NVLink; every rank copies in its own mask slab and copies out its own U,V,W slab
+            if rank == 0 or world == 1:
+                dp.copy_(hp, non_blocking=True)
+                dv.copy_(hv, non_blocking=True)
+            if world > 1:
+                dist.broadcast(dp, 0)
+                dist.broadcast(dv, 0)
             dm.copy_(hm, non_blocking=True)
             dax.copy_(hax, non_blocking=True)
             eng.build(dp, dv)
@@ -338,11 +344,12 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_ms = float(t2.item()) / n_e2e
-        h2d = hp.numel() * 8 + hv.numel() * 8 + hm.numel() + hax.numel() * 8
+        h2d = hp.numel() * 8 + hv.numel() * 8 + hm.numel() + hax.numel() * 8  # rank 0; other ranks: mask slab + axes
         d2h = hout.numel() * 4 + 16
         e2e = {"value": total_pore / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "note": "per-rank bytes; pinned host buffers; result = U,V,W slab + (sum|div|, n_fluid)"}
+               "note": "rank-0 bytes; pinned host buffers; particles enter through rank 0 and are broadcast over "
+                       "NVLink when N > 1; result = U,V,W slab + (sum|div|, n_fluid)"}
         del hp, hv, hm, hout, dp, dv, dm
 
     if rank != 0:
