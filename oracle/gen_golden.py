@@ -67,6 +67,8 @@ def main():
                      ("sibson_k12", dict(method="sibson", sibson_neighbors=12)),
                      ("rbf_k20", dict(method="rbf")),
                      ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1)),
+                     ("rbf_k40", dict(method="rbf", rbf_neighbors=40)),
+                     ("rbf_k60_s001", dict(method="rbf", rbf_neighbors=60, smoothing=0.01)),
                      ("nearest", dict(method="nearest"))):
         U, V, W = ri.interpolate_field(df, grid, **kw)
         out[name] = np.stack([U, V, W], 0)

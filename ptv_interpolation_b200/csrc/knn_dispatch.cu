@@ -43,8 +43,8 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
       set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3.");
       return PTV_ERR_INVALID;
     }
-    if (k + 4 > 32) {
-      set_error("ptv_knn_interp: rbf_neighbors > 28 is not supported on the CUDA path");
+    if (k + 4 > 64) {
+      set_error("ptv_knn_interp: rbf_neighbors > 60 is not supported on the CUDA path");
       return PTV_ERR_INVALID;
     }
     if (!(rbf_smoothing >= 0.0)) { set_error("ptv_knn_interp: smoothing must be >= 0"); return PTV_ERR_INVALID; }
@@ -159,7 +159,7 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
   if (method == PTV_METHOD_RBF) {
     if ((int64_t)k > h->n) k = (int)h->n;
     if (k < 4) { set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3."); return PTV_ERR_INVALID; }
-    if (k + 4 > 32) { set_error("ptv_knn_points: rbf_neighbors > 28 is not supported on the CUDA path"); return PTV_ERR_INVALID; }
+    if (k + 4 > 64) { set_error("ptv_knn_points: rbf_neighbors > 60 is not supported on the CUDA path"); return PTV_ERR_INVALID; }
   }
   if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_points: bad out_dtype"); return PTV_ERR_INVALID; }
   if (k < 1) { set_error("ptv_knn_points: k must be >= 1"); return PTV_ERR_INVALID; }

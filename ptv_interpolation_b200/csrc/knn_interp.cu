@@ -50,44 +50,55 @@ __device__ __forceinline__ void sift_down(double* __restrict__ hk, int* __restri
 // by the voxel's warp: lane = matrix row, matrix in shared memory (row stride 33 doubles, bank
 // conflict free), Gaussian elimination with partial pivoting (the system is symmetric indefinite,
 // so no Cholesky; scipy uses LAPACK dsysv), then vec(x) . c with vec = [phi(|x-y_j|), 1, xh, yh, zh].
-static constexpr int kRbfMaxN = 32;                                   // k + 4 <= 32
-static constexpr int kRbfLd = kRbfMaxN + 1;
-static constexpr int kRbfScratchDoubles = kRbfMaxN * kRbfLd + kRbfMaxN * 3 + kRbfMaxN * 3 + kRbfMaxN / 2;
+// RPL = matrix rows per lane: 1 for k + 4 <= 32, 2 for k + 4 <= 64.
+__host__ __device__ constexpr int rbf_scratch_doubles(int rpl) {
+  return (32 * rpl) * (32 * rpl + 1) + (32 * rpl) * 3 * 2 + (32 * rpl) / 2;
+}
 
 __device__ __forceinline__ double tps_phi_from_d2(double d2) {
   // phi(r) = r^2 log r with phi(0) = 0 (_rbfinterp_xp.py:98-100); r^2 log r == 0.5 * d2 * log(d2)
   return d2 > 0.0 ? 0.5 * d2 * log(d2) : 0.0;
 }
 
-template <int T>
+template <int T, int RPL>
 __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratch, const double* hkey_all,
                                  const int* hidx_all, double qx, double qy, double qz, bool active, double& su,
                                  double& sv, double& sw) {
+  constexpr int NMAX = 32 * RPL, LD = NMAX + 1;
   const unsigned full = 0xffffffffu;
   const int t = threadIdx.x, lane = t & 31, wbase = t & ~31;
   const int k = p.k, n = k + 4;
-  double* A = scratch;                       // [32][33]
-  double* B = A + kRbfMaxN * kRbfLd;         // [32][3] right-hand sides -> coefficients
-  double* Y = B + kRbfMaxN * 3;              // [32][3] neighbour coordinates
-  int* perm = reinterpret_cast<int*>(Y + kRbfMaxN * 3);  // [32] pivot row of each column
+  double* A = scratch;                    // [NMAX][LD]
+  double* B = A + NMAX * LD;              // [NMAX][3] right-hand sides -> coefficients
+  double* Y = B + NMAX * 3;               // [NMAX][3] neighbour coordinates
+  int* perm = reinterpret_cast<int*>(Y + NMAX * 3);  // [NMAX] pivot row of each column
   const HashGrid& g = p.g;
   for (int v = 0; v < 32; ++v) {
     if (!__shfl_sync(full, active ? 1 : 0, v)) continue;
     const double vx = __shfl_sync(full, qx, v), vy = __shfl_sync(full, qy, v), vz = __shfl_sync(full, qz, v);
-    // lane j < k owns neighbour j of voxel v
-    double yx = 0.0, yy = 0.0, yz = 0.0, d2q = 0.0;
-    Value4 val; val.u = val.v = val.w = val.pad = 0.0;
-    if (lane < k) {
-      const int pj = hidx_all[lane * T + wbase + v];
-      d2q = hkey_all[lane * T + wbase + v];
-      yx = g.pts[(int64_t)pj * 3 + 0];
-      yy = g.pts[(int64_t)pj * 3 + 1];
-      yz = g.pts[(int64_t)pj * 3 + 2];
-      val = g.vals[pj];
+    // row r = lane + 32*q; rows < k own neighbour r of voxel v
+    double yx[RPL], yy[RPL], yz[RPL], d2q[RPL];
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const int r = lane + 32 * q;
+      yx[q] = yy[q] = yz[q] = d2q[q] = 0.0;
+      if (r < k) {
+        const int pj = hidx_all[r * T + wbase + v];
+        d2q[q] = hkey_all[r * T + wbase + v];
+        yx[q] = g.pts[(int64_t)pj * 3 + 0];
+        yy[q] = g.pts[(int64_t)pj * 3 + 1];
+        yz[q] = g.pts[(int64_t)pj * 3 + 2];
+        const Value4 val = g.vals[pj];
+        B[r * 3 + 0] = val.u; B[r * 3 + 1] = val.v; B[r * 3 + 2] = val.w;
+        Y[r * 3 + 0] = yx[q]; Y[r * 3 + 1] = yy[q]; Y[r * 3 + 2] = yz[q];
+        mn[0] = fmin(mn[0], yx[q]); mn[1] = fmin(mn[1], yy[q]); mn[2] = fmin(mn[2], yz[q]);
+        mx[0] = fmax(mx[0], yx[q]); mx[1] = fmax(mx[1], yy[q]); mx[2] = fmax(mx[2], yz[q]);
+      } else if (r < n) {
+        B[r * 3 + 0] = 0.0; B[r * 3 + 1] = 0.0; B[r * 3 + 2] = 0.0;
+      }
     }
     // shift / scale of the neighbourhood (_rbfinterp_xp.py:186-193)
-    double mn[3] = {lane < k ? yx : INFINITY, lane < k ? yy : INFINITY, lane < k ? yz : INFINITY};
-    double mx[3] = {lane < k ? yx : -INFINITY, lane < k ? yy : -INFINITY, lane < k ? yz : -INFINITY};
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -103,38 +114,51 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
       scale[c] = (mx[c] - mn[c]) / 2.0;
       if (scale[c] == 0.0) scale[c] = 1.0;
     }
-    if (lane < k) {
-      Y[lane * 3 + 0] = yx; Y[lane * 3 + 1] = yy; Y[lane * 3 + 2] = yz;
-    }
     __syncwarp();
-    if (lane < k) {
-      double* row = A + lane * kRbfLd;
-      for (int j = 0; j < k; ++j) {
-        const double dx = yx - Y[j * 3 + 0], dy = yy - Y[j * 3 + 1], dz = yz - Y[j * 3 + 2];
-        row[j] = tps_phi_from_d2((dx * dx + dy * dy) + dz * dz);
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {  // kernel rows: K + sI | P
+      const int r = lane + 32 * q;
+      if (r < k) {
+        double* row = A + r * LD;
+        for (int j = 0; j < k; ++j) {
+          const double dx = yx[q] - Y[j * 3 + 0], dy = yy[q] - Y[j * 3 + 1], dz = yz[q] - Y[j * 3 + 2];
+          row[j] = tps_phi_from_d2((dx * dx + dy * dy) + dz * dz);
+        }
+        row[r] += p.smoothing;
+        row[k + 0] = 1.0;
+        row[k + 1] = (yx[q] - shift[0]) / scale[0];
+        row[k + 2] = (yy[q] - shift[1]) / scale[1];
+        row[k + 3] = (yz[q] - shift[2]) / scale[2];
       }
-      row[lane] += p.smoothing;
-      row[k + 0] = 1.0;
-      row[k + 1] = (yx - shift[0]) / scale[0];
-      row[k + 2] = (yy - shift[1]) / scale[1];
-      row[k + 3] = (yz - shift[2]) / scale[2];
-      B[lane * 3 + 0] = val.u; B[lane * 3 + 1] = val.v; B[lane * 3 + 2] = val.w;
     }
     __syncwarp();
-    if (lane >= k && lane < n) {  // polynomial rows: P^T | 0
-      double* row = A + lane * kRbfLd;
-      for (int j = 0; j < k; ++j) row[j] = A[j * kRbfLd + lane];
-      for (int j = k; j < n; ++j) row[j] = 0.0;
-      B[lane * 3 + 0] = 0.0; B[lane * 3 + 1] = 0.0; B[lane * 3 + 2] = 0.0;
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {  // polynomial rows: P^T | 0
+      const int r = lane + 32 * q;
+      if (r >= k && r < n) {
+        double* row = A + r * LD;
+        for (int j = 0; j < k; ++j) row[j] = A[j * LD + r];
+        for (int j = k; j < n; ++j) row[j] = 0.0;
+      }
     }
     __syncwarp();
     // ---- elimination with partial pivoting; rows stay in place, perm[col] = pivot row
-    bool used = false;
-    int my_col = n;  // column this row pivots (n = not yet)
+    bool used[RPL];
+    int my_col[RPL];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) { used[q] = false; my_col[q] = n; }
     bool singular = false;
     for (int c = 0; c < n; ++c) {
-      double bv = (lane < n && !used) ? fabs(A[lane * kRbfLd + c]) : -1.0;
-      int best = lane;
+      double bv = -1.0;
+      int best = NMAX;
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        const int r = lane + 32 * q;
+        if (r < n && !used[q]) {
+          const double a = fabs(A[r * LD + c]);
+          if (a > bv) { bv = a; best = r; }  // NaN compares false: never chosen, caught below
+        }
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(full, bv, o);
@@ -142,17 +166,23 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
         if (ov > bv || (ov == bv && ol < best)) { bv = ov; best = ol; }
       }
       if (!(bv > 0.0)) { singular = true; break; }  // exact zero (or NaN) pivot column: dsysv info > 0
-      if (lane == best) { used = true; my_col = c; perm[c] = lane; }
-      const double* prow = A + best * kRbfLd;
+#pragma unroll
+      for (int q = 0; q < RPL; ++q)
+        if (lane + 32 * q == best) { used[q] = true; my_col[q] = c; perm[c] = best; }
+      const double* prow = A + best * LD;
       const double piv = prow[c];
-      if (lane < n && !used) {
-        double* row = A + lane * kRbfLd;
-        const double f = row[c] / piv;
-        if (f != 0.0) {
-          for (int j = c + 1; j < n; ++j) row[j] -= f * prow[j];
-          B[lane * 3 + 0] -= f * B[best * 3 + 0];
-          B[lane * 3 + 1] -= f * B[best * 3 + 1];
-          B[lane * 3 + 2] -= f * B[best * 3 + 2];
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        const int r = lane + 32 * q;
+        if (r < n && !used[q]) {
+          double* row = A + r * LD;
+          const double f = row[c] / piv;
+          if (f != 0.0) {
+            for (int j = c + 1; j < n; ++j) row[j] -= f * prow[j];
+            B[r * 3 + 0] -= f * B[best * 3 + 0];
+            B[r * 3 + 1] -= f * B[best * 3 + 1];
+            B[r * 3 + 2] -= f * B[best * 3 + 2];
+          }
         }
       }
       __syncwarp();
@@ -164,28 +194,36 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
     }
     // ---- back substitution: the row pivoting column c holds unknown c
     for (int c = n - 1; c >= 0; --c) {
-      const int r = perm[c];
-      const double inv = 1.0 / A[r * kRbfLd + c];
-      const double x0 = B[r * 3 + 0] * inv, x1 = B[r * 3 + 1] * inv, x2 = B[r * 3 + 2] * inv;
+      const int pr = perm[c];
+      const double inv = 1.0 / A[pr * LD + c];
+      const double x0 = B[pr * 3 + 0] * inv, x1 = B[pr * 3 + 1] * inv, x2 = B[pr * 3 + 2] * inv;
       __syncwarp();
-      if (lane == r) { B[r * 3 + 0] = x0; B[r * 3 + 1] = x1; B[r * 3 + 2] = x2; }
-      if (lane < n && my_col < c) {
-        const double a = A[lane * kRbfLd + c];
-        B[lane * 3 + 0] -= a * x0; B[lane * 3 + 1] -= a * x1; B[lane * 3 + 2] -= a * x2;
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        const int r = lane + 32 * q;
+        if (r == pr) { B[r * 3 + 0] = x0; B[r * 3 + 1] = x1; B[r * 3 + 2] = x2; }
+        else if (r < n && my_col[q] < c) {
+          const double a = A[r * LD + c];
+          B[r * 3 + 0] -= a * x0; B[r * 3 + 1] -= a * x1; B[r * 3 + 2] -= a * x2;
+        }
       }
       __syncwarp();
     }
-    // ---- evaluate vec(x) . coeffs (_rbfinterp_xp.py:213-266); lane j holds unknown j's weight
+    // ---- evaluate vec(x) . coeffs (_rbfinterp_xp.py:213-266); row j holds unknown j's weight
     double e0 = 0.0, e1 = 0.0, e2 = 0.0;
-    if (lane < n) {
-      double vj;
-      if (lane < k) vj = tps_phi_from_d2(d2q);
-      else if (lane == k) vj = 1.0;
-      else if (lane == k + 1) vj = (vx - shift[0]) / scale[0];
-      else if (lane == k + 2) vj = (vy - shift[1]) / scale[1];
-      else vj = (vz - shift[2]) / scale[2];
-      const int r = perm[lane];
-      e0 = vj * B[r * 3 + 0]; e1 = vj * B[r * 3 + 1]; e2 = vj * B[r * 3 + 2];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const int r = lane + 32 * q;
+      if (r < n) {
+        double vj;
+        if (r < k) vj = tps_phi_from_d2(d2q[q]);
+        else if (r == k) vj = 1.0;
+        else if (r == k + 1) vj = (vx - shift[0]) / scale[0];
+        else if (r == k + 2) vj = (vy - shift[1]) / scale[1];
+        else vj = (vz - shift[2]) / scale[2];
+        const int pr = perm[r];
+        e0 += vj * B[pr * 3 + 0]; e1 += vj * B[pr * 3 + 1]; e2 += vj * B[pr * 3 + 2];
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -198,7 +236,7 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
   }
 }
 
-template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf>
+template <int T, int TX, int TY, int TZ, typename OutT, int kRbf>  // kRbf: 0 = no RBF, else matrix rows per lane
 __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, unsigned char* smem_raw) {
   static_assert(TX * TY * TZ == T, "tile shape");
   constexpr int NW = T / 32;
@@ -211,7 +249,7 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
   int* seg_off = seg_start + T;                                         // [T+1]
   int* warp_tot = seg_off + T + 1;                                      // [NW]
   double* rbf_scratch = reinterpret_cast<double*>(
-      (reinterpret_cast<uintptr_t>(warp_tot + NW) + 15) & ~(uintptr_t)15);  // [NW][kRbfScratchDoubles], RBF only
+      (reinterpret_cast<uintptr_t>(warp_tot + NW) + 15) & ~(uintptr_t)15);  // [NW][rbf_scratch_doubles], RBF only
 
   const int t = threadIdx.x;
   double* hk = hkey_all + t;
@@ -322,8 +360,8 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
 
   if (kRbf) {
     // every lane of the warp helps to solve each voxel's local system, so no early exits here
-    rbf_tps_epilogue<T>(p, rbf_scratch + (size_t)(t >> 5) * kRbfScratchDoubles, hkey_all, hidx_all, qx, qy, qz,
-                        active && kk == k, su, sv, sw);
+    rbf_tps_epilogue<T, (kRbf > 0 ? kRbf : 1)>(p, rbf_scratch + (size_t)(t >> 5) * rbf_scratch_doubles(kRbf > 0 ? kRbf : 1),
+                                               hkey_all, hidx_all, qx, qy, qz, active && kk == k, su, sv, sw);
   }
 
   if (!valid) return;
@@ -473,7 +511,7 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
 
 // One CTA per tile, or -- when the streaming kernel handed over a fail list -- a fixed grid of CTAs
 // striding over the listed tiles.
-template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf>
+template <int T, int TX, int TY, int TZ, typename OutT, int kRbf>
 __global__ void __launch_bounds__(T, 2) knn_interp_kernel(const KnnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (p.tile_list == nullptr) {
@@ -494,11 +532,11 @@ size_t knn_heap_smem_bytes(int T, int k, int method) {
              (size_t)6 * NW * sizeof(double) + (size_t)k * T * sizeof(int) +
              (size_t)(2 * T + 1 + NW) * sizeof(int);
   b = (b + 15) & ~(size_t)15;
-  if (method == PTV_METHOD_RBF) b += 16 + (size_t)NW * kRbfScratchDoubles * sizeof(double);
+  if (method == PTV_METHOD_RBF) b += 16 + (size_t)NW * rbf_scratch_doubles(k + 4 <= 32 ? 1 : 2) * sizeof(double);
   return (b + 15) & ~(size_t)15;
 }
 
-template <int T, int TX, int TY, int TZ, typename OutT, bool kRbf = false>
+template <int T, int TX, int TY, int TZ, typename OutT, int kRbf = 0>
 static int launch_knn(KnnParams& p, cudaStream_t stream) {
   p.tiles_x = (p.nx + TX - 1) / TX;
   p.tiles_y = (p.ny + TY - 1) / TY;
@@ -521,8 +559,12 @@ static int launch_knn(KnnParams& p, cudaStream_t stream) {
 }
 
 int launch_knn_heap(KnnParams& p, int T, bool f32, cudaStream_t stream) {
-  if (p.method == PTV_METHOD_RBF)
-    return f32 ? launch_knn<128, 8, 4, 4, float, true>(p, stream) : launch_knn<128, 8, 4, 4, double, true>(p, stream);
+  if (p.method == PTV_METHOD_RBF) {
+    if (p.k + 4 <= 32)
+      return f32 ? launch_knn<128, 8, 4, 4, float, 1>(p, stream) : launch_knn<128, 8, 4, 4, double, 1>(p, stream);
+    // up to 60 neighbours: two matrix rows per lane, 64-voxel tiles so the 64x65 systems fit in shared memory
+    return f32 ? launch_knn<64, 4, 4, 4, float, 2>(p, stream) : launch_knn<64, 4, 4, 4, double, 2>(p, stream);
+  }
   switch (T) {
     case 128: return f32 ? launch_knn<128, 8, 4, 4, float>(p, stream) : launch_knn<128, 8, 4, 4, double>(p, stream);
     case 64: return f32 ? launch_knn<64, 4, 4, 4, float>(p, stream) : launch_knn<64, 4, 4, 4, double>(p, stream);

@@ -359,7 +359,9 @@ def test_host_cabi_entry_point():
 
 # ------------------------------------------------------------------ local RBF (a8/a9)
 @pytest.mark.parametrize("name,kw", [("rbf_k20", dict(method="rbf")),
-                                     ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1))])
+                                     ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1)),
+                                     ("rbf_k40", dict(method="rbf", rbf_neighbors=40)),
+                                     ("rbf_k60_s001", dict(method="rbf", rbf_neighbors=60, smoothing=0.01))])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_golden_rbf(case_a, name, kw, dtype):
     g, grid, df = case_a
@@ -403,6 +405,8 @@ def test_rbf_sphere_pack_vs_oracle_and_errors():
         gi.interpolate_field(_df(flat, vals[:300]), grid, method="rbf")
     with pytest.raises(ValueError):  # fewer than 4 points: RBFInterpolator raises ValueError
         gi.interpolate_field(_df(pts[:3], vals[:3]), grid, method="rbf")
+    with pytest.raises(ValueError):  # documented limit of the CUDA path
+        gi.interpolate_field(_df(pts, vals), grid, method="rbf", rbf_neighbors=61)
 
 
 # ------------------------------------------------------------------ BASELINE-size checks (c2 / c3 geometry)

@@ -45,6 +45,8 @@ def test_knn_matches_ckdtree_and_bruteforce(golden_dir, k):
     ("sibson_k12", dict(method="sibson", sibson_neighbors=12)),
     ("rbf_k20", dict(method="rbf")),
     ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1)),
+    ("rbf_k40", dict(method="rbf", rbf_neighbors=40)),
+    ("rbf_k60_s001", dict(method="rbf", rbf_neighbors=60, smoothing=0.01)),
     ("nearest", dict(method="nearest")),
 ])
 def test_interpolate_field_bitexact(golden_dir, name, kw):
