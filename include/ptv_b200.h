@@ -43,6 +43,11 @@ extern "C" {
 #define PTV_METHOD_NEAREST 2 /* interpolator.py:197 griddata(method='nearest') == k=1 */
 #define PTV_METHOD_RBF 3     /* interpolator.py:157-195 local thin-plate-spline RBF */
 #define PTV_METHOD_MADFILTER 4 /* internal: filtering.py:5-58, reached through ptv_outlier_filter */
+/* local RBF with the other scale-invariant kernels RBFInterpolator accepts without epsilon
+ * (interpolator.py:162-167 passes rbf_kernel through): minimum polynomial degree 1 / 0 / 2 */
+#define PTV_METHOD_RBF_CUBIC 5
+#define PTV_METHOD_RBF_LINEAR 6
+#define PTV_METHOD_RBF_QUINTIC 7
 
 /* output element types for the velocity grids */
 #define PTV_F32 0

@@ -13,6 +13,7 @@ import numpy as np
 
 PTV_OK, PTV_ERR_INVALID, PTV_ERR_TOO_FEW, PTV_ERR_CUDA, PTV_ERR_SINGULAR, PTV_ERR_NOMEM = range(6)
 METHOD_IDW, METHOD_SIBSON, METHOD_NEAREST, METHOD_RBF, METHOD_MADFILTER = range(5)
+METHOD_RBF_CUBIC, METHOD_RBF_LINEAR, METHOD_RBF_QUINTIC = 5, 6, 7
 F32, F64 = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -27,6 +27,8 @@ struct KnnParams {
   int r0;
   double rscale;  // stream kernel: first scan radius^2 = rscale * r_est^2
   double smoothing;
+  int rbf_kernel;  // 0 thin_plate_spline, 1 cubic, 2 linear, 3 quintic
+  int rbf_npoly;   // monomials of the polynomial tail: 4 (degree 1), 1 (degree 0), 10 (degree 2)
   int* err_flag;
   // stream kernel -> heap kernel hand-off: tiles the optimistic kernel could not finish
   int* fail_list;        // [capacity]

@@ -18,6 +18,35 @@ static int ensure_fail_buffers(ptv_hash* h, int64_t ntiles) {
   return PTV_OK;
 }
 
+// PTV_METHOD_RBF* -> (PTV_METHOD_RBF, kernel id, monomials of the tail, minimum degree)
+static bool rbf_variant(int& method, int& kern, int& npoly, int& degree) {
+  kern = 0; npoly = 4; degree = 1;
+  switch (method) {
+    case PTV_METHOD_RBF: return true;
+    case PTV_METHOD_RBF_CUBIC: kern = 1; break;
+    case PTV_METHOD_RBF_LINEAR: kern = 2; npoly = 1; degree = 0; break;
+    case PTV_METHOD_RBF_QUINTIC: kern = 3; npoly = 10; degree = 2; break;
+    default: return false;
+  }
+  method = PTV_METHOD_RBF;
+  return true;
+}
+
+static int rbf_check(int64_t n_particles, int& k, int npoly, int degree, double smoothing, const char* who) {
+  if ((int64_t)k > n_particles) k = (int)n_particles;  // RBFInterpolator clamps neighbors to Np (scipy _rbfinterp.py:313)
+  if (k < npoly) {
+    set_error("At least " + std::to_string(npoly) + " data points are required when `degree` is " +
+              std::to_string(degree) + " and the number of dimensions is 3.");
+    return PTV_ERR_INVALID;
+  }
+  if (k + npoly > 64) {
+    set_error(std::string(who) + ": rbf_neighbors > " + std::to_string(64 - npoly) + " is not supported on the CUDA path");
+    return PTV_ERR_INVALID;
+  }
+  if (!(smoothing >= 0.0)) { set_error(std::string(who) + ": smoothing must be >= 0"); return PTV_ERR_INVALID; }
+  return PTV_OK;
+}
+
 static void tile_shape(int T, int& tx, int& ty, int& tz) {
   tx = T == 128 ? 8 : 4; ty = 4; tz = T == 32 ? 2 : 4;
 }
@@ -32,22 +61,15 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_knn_interp: empty grid"); return PTV_ERR_INVALID; }
   if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_interp: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
   if (method == PTV_METHOD_NEAREST) k = 1;
-  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST &&
-      method != PTV_METHOD_RBF) {
+  int rbf_kern = 0, rbf_npoly = 4, rbf_degree = 1;
+  const bool is_rbf = rbf_variant(method, rbf_kern, rbf_npoly, rbf_degree);
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST && !is_rbf) {
     set_error("ptv_knn_interp: unsupported method");
     return PTV_ERR_INVALID;
   }
-  if (method == PTV_METHOD_RBF) {
-    if ((int64_t)k > h->n) k = (int)h->n;  // RBFInterpolator clamps neighbors to Np (scipy _rbfinterp.py:313)
-    if (k < 4) {
-      set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3.");
-      return PTV_ERR_INVALID;
-    }
-    if (k + 4 > 64) {
-      set_error("ptv_knn_interp: rbf_neighbors > 60 is not supported on the CUDA path");
-      return PTV_ERR_INVALID;
-    }
-    if (!(rbf_smoothing >= 0.0)) { set_error("ptv_knn_interp: smoothing must be >= 0"); return PTV_ERR_INVALID; }
+  if (is_rbf) {
+    const int rc0 = rbf_check(h->n, k, rbf_npoly, rbf_degree, rbf_smoothing, "ptv_knn_interp");
+    if (rc0 != PTV_OK) return rc0;
   }
   if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_interp: bad out_dtype"); return PTV_ERR_INVALID; }
   if (k < 1) { set_error("ptv_knn_interp: k must be >= 1"); return PTV_ERR_INVALID; }
@@ -66,6 +88,8 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
   p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
   p.smoothing = rbf_smoothing;
+  p.rbf_kernel = rbf_kern;
+  p.rbf_npoly = rbf_npoly;
   p.rscale = tuning().rscale;
   p.err_flag = h->err_flag;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
@@ -132,6 +156,8 @@ static void init_point_params(KnnParams& p, const ptv_hash* h, const ptv_hash* q
   p.r0 = tuning().r0 < 0 ? 0 : tuning().r0;
   p.rscale = tuning().rscale;
   p.smoothing = 0.0;
+  p.rbf_kernel = 0;
+  p.rbf_npoly = 4;
   p.err_flag = h->err_flag;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.qrec = q->rec; p.nq = q->n;
@@ -154,12 +180,15 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
   if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_points: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
   if (!want_uvw && !d_knn_idx) { set_error("ptv_knn_points: nothing to compute"); return PTV_ERR_INVALID; }
   if (method == PTV_METHOD_NEAREST) k = 1;
-  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST &&
-      method != PTV_METHOD_RBF) { set_error("ptv_knn_points: unsupported method"); return PTV_ERR_INVALID; }
-  if (method == PTV_METHOD_RBF) {
-    if ((int64_t)k > h->n) k = (int)h->n;
-    if (k < 4) { set_error("At least 4 data points are required when `degree` is 1 and the number of dimensions is 3."); return PTV_ERR_INVALID; }
-    if (k + 4 > 64) { set_error("ptv_knn_points: rbf_neighbors > 60 is not supported on the CUDA path"); return PTV_ERR_INVALID; }
+  int rbf_kern = 0, rbf_npoly = 4, rbf_degree = 1;
+  const bool is_rbf = rbf_variant(method, rbf_kern, rbf_npoly, rbf_degree);
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST && !is_rbf) {
+    set_error("ptv_knn_points: unsupported method");
+    return PTV_ERR_INVALID;
+  }
+  if (is_rbf) {
+    const int rc0 = rbf_check(h->n, k, rbf_npoly, rbf_degree, rbf_smoothing, "ptv_knn_points");
+    if (rc0 != PTV_OK) return rc0;
   }
   if (out_dtype != PTV_F32 && out_dtype != PTV_F64) { set_error("ptv_knn_points: bad out_dtype"); return PTV_ERR_INVALID; }
   if (k < 1) { set_error("ptv_knn_points: k must be >= 1"); return PTV_ERR_INVALID; }
@@ -171,6 +200,7 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
   KnnParams p;
   init_point_params(p, h, queries);
   p.method = method; p.k = k; p.power = idw_power; p.smoothing = rbf_smoothing;
+  p.rbf_kernel = rbf_kern; p.rbf_npoly = rbf_npoly;
   // u, v, w are always written by the kernel: give it scratch when only the lists are wanted
   void* scratch = nullptr;
   if (!want_uvw) {

@@ -55,9 +55,30 @@ __host__ __device__ constexpr int rbf_scratch_doubles(int rpl) {
   return (32 * rpl) * (32 * rpl + 1) + (32 * rpl) * 3 * 2 + (32 * rpl) / 2;
 }
 
-__device__ __forceinline__ double tps_phi_from_d2(double d2) {
-  // phi(r) = r^2 log r with phi(0) = 0 (_rbfinterp_xp.py:98-100); r^2 log r == 0.5 * d2 * log(d2)
-  return d2 > 0.0 ? 0.5 * d2 * log(d2) : 0.0;
+// Scale-invariant kernels of scipy.interpolate.RBFInterpolator (the only ones the reference can reach:
+// it never passes epsilon, _rbfinterp.py:280-289) as functions of d2 = r^2 (_rbfinterp_xp.py:93-110):
+// 0 thin_plate_spline r^2 log r (phi(0) = 0), 1 cubic r^3, 2 linear -r, 3 quintic -r^5.
+__device__ __forceinline__ double rbf_phi_from_d2(int kern, double d2) {
+  if (kern == 0) return d2 > 0.0 ? 0.5 * d2 * log(d2) : 0.0;
+  const double r = sqrt(d2);
+  if (kern == 1) return d2 * r;
+  if (kern == 2) return -r;
+  return -(d2 * d2 * r);
+}
+// Monomials of degree <= 2 in scipy's order (_rbfinterp_common.py:5-32): 1, x, y, z, xx, xy, xz, yy, yz, zz
+__device__ __forceinline__ double rbf_monomial(int m, double x, double y, double z) {
+  switch (m) {
+    case 0: return 1.0;
+    case 1: return x;
+    case 2: return y;
+    case 3: return z;
+    case 4: return x * x;
+    case 5: return x * y;
+    case 6: return x * z;
+    case 7: return y * y;
+    case 8: return y * z;
+    default: return z * z;
+  }
 }
 
 template <int T, int RPL>
@@ -67,7 +88,7 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
   constexpr int NMAX = 32 * RPL, LD = NMAX + 1;
   const unsigned full = 0xffffffffu;
   const int t = threadIdx.x, lane = t & 31, wbase = t & ~31;
-  const int k = p.k, n = k + 4;
+  const int k = p.k, npoly = p.rbf_npoly, n = k + npoly, kern = p.rbf_kernel;
   double* A = scratch;                    // [NMAX][LD]
   double* B = A + NMAX * LD;              // [NMAX][3] right-hand sides -> coefficients
   double* Y = B + NMAX * 3;               // [NMAX][3] neighbour coordinates
@@ -122,13 +143,12 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
         double* row = A + r * LD;
         for (int j = 0; j < k; ++j) {
           const double dx = yx[q] - Y[j * 3 + 0], dy = yy[q] - Y[j * 3 + 1], dz = yz[q] - Y[j * 3 + 2];
-          row[j] = tps_phi_from_d2((dx * dx + dy * dy) + dz * dz);
+          row[j] = rbf_phi_from_d2(kern, (dx * dx + dy * dy) + dz * dz);
         }
         row[r] += p.smoothing;
-        row[k + 0] = 1.0;
-        row[k + 1] = (yx[q] - shift[0]) / scale[0];
-        row[k + 2] = (yy[q] - shift[1]) / scale[1];
-        row[k + 3] = (yz[q] - shift[2]) / scale[2];
+        const double hx = (yx[q] - shift[0]) / scale[0], hy = (yy[q] - shift[1]) / scale[1],
+                     hz = (yz[q] - shift[2]) / scale[2];
+        for (int m = 0; m < npoly; ++m) row[k + m] = rbf_monomial(m, hx, hy, hz);
       }
     }
     __syncwarp();
@@ -216,11 +236,8 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
       const int r = lane + 32 * q;
       if (r < n) {
         double vj;
-        if (r < k) vj = tps_phi_from_d2(d2q[q]);
-        else if (r == k) vj = 1.0;
-        else if (r == k + 1) vj = (vx - shift[0]) / scale[0];
-        else if (r == k + 2) vj = (vy - shift[1]) / scale[1];
-        else vj = (vz - shift[2]) / scale[2];
+        if (r < k) vj = rbf_phi_from_d2(kern, d2q[q]);
+        else vj = rbf_monomial(r - k, (vx - shift[0]) / scale[0], (vy - shift[1]) / scale[1], (vz - shift[2]) / scale[2]);
         const int pr = perm[r];
         e0 += vj * B[pr * 3 + 0]; e1 += vj * B[pr * 3 + 1]; e2 += vj * B[pr * 3 + 2];
       }
@@ -532,7 +549,7 @@ size_t knn_heap_smem_bytes(int T, int k, int method) {
              (size_t)6 * NW * sizeof(double) + (size_t)k * T * sizeof(int) +
              (size_t)(2 * T + 1 + NW) * sizeof(int);
   b = (b + 15) & ~(size_t)15;
-  if (method == PTV_METHOD_RBF) b += 16 + (size_t)NW * rbf_scratch_doubles(k + 4 <= 32 ? 1 : 2) * sizeof(double);
+  if (method == PTV_METHOD_RBF) b += 16 + (size_t)NW * rbf_scratch_doubles(k + 10 <= 32 ? 1 : 2) * sizeof(double);  // sized for the largest tail
   return (b + 15) & ~(size_t)15;
 }
 
@@ -560,7 +577,7 @@ static int launch_knn(KnnParams& p, cudaStream_t stream) {
 
 int launch_knn_heap(KnnParams& p, int T, bool f32, cudaStream_t stream) {
   if (p.method == PTV_METHOD_RBF) {
-    if (p.k + 4 <= 32)
+    if (p.k + p.rbf_npoly <= 32)
       return f32 ? launch_knn<128, 8, 4, 4, float, 1>(p, stream) : launch_knn<128, 8, 4, 4, double, 1>(p, stream);
     // up to 60 neighbours: two matrix rows per lane, 64-voxel tiles so the 64x65 systems fit in shared memory
     return f32 ? launch_knn<64, 4, 4, 4, float, 2>(p, stream) : launch_knn<64, 4, 4, 4, double, 2>(p, stream);

@@ -15,6 +15,25 @@ from . import _cabi
 
 _METHODS = {"idw": _cabi.METHOD_IDW, "sibson": _cabi.METHOD_SIBSON, "nearest": _cabi.METHOD_NEAREST,
             "rbf": _cabi.METHOD_RBF}
+# scipy.interpolate.RBFInterpolator kernels usable without `epsilon` (the reference never passes one)
+_RBF_KERNELS = {"thin_plate_spline": _cabi.METHOD_RBF, "cubic": _cabi.METHOD_RBF_CUBIC,
+                "linear": _cabi.METHOD_RBF_LINEAR, "quintic": _cabi.METHOD_RBF_QUINTIC}
+_RBF_NEED_EPSILON = ("multiquadric", "inverse_multiquadric", "inverse_quadratic", "gaussian")
+
+
+def method_code(method: str, rbf_kernel: str = "thin_plate_spline") -> int:
+    """C ABI method code; mirrors RBFInterpolator's argument checks (_rbfinterp.py:276-289)."""
+    if method not in _METHODS:
+        raise NotImplementedError(f"method {method!r} is not on the CUDA path")
+    if method != "rbf":
+        return _METHODS[method]
+    kern = str(rbf_kernel).lower()
+    if kern in _RBF_KERNELS:
+        return _RBF_KERNELS[kern]
+    if kern in _RBF_NEED_EPSILON:
+        raise ValueError("`epsilon` must be specified if `kernel` is not one of "
+                         "{'linear', 'thin_plate_spline', 'cubic', 'quintic'}.")
+    raise ValueError(f"`kernel` must be one of {sorted(list(_RBF_KERNELS) + list(_RBF_NEED_EPSILON))}.")
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -91,12 +110,11 @@ class PTVEngine:
 
     # ------------------------------------------------------------------ interpolation
     def interpolate(self, ax_x, ax_y, ax_z, mask=None, method="idw", k=50, idw_power=2.0, smoothing=0.0,
-                    out_dtype=torch.float32, out=None, return_knn=False):
+                    out_dtype=torch.float32, out=None, return_knn=False, rbf_kernel="thin_plate_spline"):
         """Fused kNN + weights on the rectilinear grid ax_x (x) ax_y (x) ax_z (float64 CUDA axes).
         mask: optional (nz,ny,nx) uint8/bool CUDA tensor, non-zero = pore.  Returns a (3,nz,ny,nx)
         tensor (U,V,W) and, if ``return_knn``, (dist (nvox,k) float64, idx (nvox,k) int64)."""
-        if method not in _METHODS:
-            raise NotImplementedError(f"method {method!r} is not on the CUDA path")
+        code = method_code(method, rbf_kernel)
         nx, ny, nz = ax_x.numel(), ax_y.numel(), ax_z.numel()
         for a in (ax_x, ax_y, ax_z):
             if a.dtype != torch.float64 or not a.is_cuda:
@@ -120,7 +138,7 @@ class PTVEngine:
             kd = torch.empty((nz * ny * nx, k), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.ptv_knn_interp(self._h, _ptr(ax_x), nx, _ptr(ax_y), ny, _ptr(ax_z), nz, _ptr(mask),
-                                                _METHODS[method], int(k), float(idw_power), float(smoothing),
+                                                code, int(k), float(idw_power), float(smoothing),
                                                 _dtype_code(out.dtype), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
                                                 _ptr(ki), _ptr(kd), self._stream()))
         if return_knn:
@@ -158,12 +176,11 @@ class PTVEngine:
         return dev_out
 
     def interpolate_points(self, queries: "PTVEngine", method="idw", k=50, idw_power=2.0, smoothing=0.0,
-                           out_dtype=torch.float32, return_knn=False, values=True):
+                           out_dtype=torch.float32, return_knn=False, values=True, rbf_kernel="thin_plate_spline"):
         """The same search / weights for arbitrary query points: ``queries`` is a second engine whose
         hash was built over the query points (pass ``self`` for a self-query).  Returns a (3, nq) tensor
         indexed by the query's original row (and (dist, idx) (nq,k) if ``return_knn``)."""
-        if method not in _METHODS:
-            raise NotImplementedError(f"method {method!r} is not on the CUDA path")
+        code = method_code(method, rbf_kernel)
         nq = queries.n_particles
         if method == "nearest":
             k = 1
@@ -174,7 +191,7 @@ class PTVEngine:
             kd = torch.empty((nq, k), dtype=torch.float64, device=self.device)
         o = [None, None, None] if out is None else [out[0], out[1], out[2]]
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.ptv_knn_points(self._h, queries._h, _METHODS[method], int(k), float(idw_power),
+            _cabi.check(self.lib.ptv_knn_points(self._h, queries._h, code, int(k), float(idw_power),
                                                 float(smoothing), _dtype_code(out_dtype), _ptr(o[0]), _ptr(o[1]),
                                                 _ptr(o[2]), _ptr(ki), _ptr(kd), self._stream()))
         if return_knn:

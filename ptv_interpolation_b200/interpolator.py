@@ -104,14 +104,15 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
         raise NotImplementedError(
             f"method={method!r} (scipy griddata / Delaunay, interpolator.py:197) is not implemented on the "
             f"CUDA path; supported methods: {_GPU_METHODS}")
-    if method == "rbf" and rbf_kernel != "thin_plate_spline":
-        raise NotImplementedError("only rbf_kernel='thin_plate_spline' is on the CUDA path")
+    if method == "rbf":
+        from .engine import method_code
+        method_code("rbf", rbf_kernel)  # RBFInterpolator's kernel / epsilon checks (ValueError)
     axes = _grid_axes(grid_tuple)
     eng = default_engine(device)
     dev = eng.device
     if axes is None:
         return _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,
-                                      idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn)
+                                      idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn, rbf_kernel)
     x, y, z = axes
     pts = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev)
     vals = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
@@ -124,7 +125,7 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     if mask is not None:
         m = torch.from_numpy(np.ascontiguousarray(mask).astype(np.uint8, copy=False)).to(dev)
     tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
-    kw = dict(method=method, k=int(k), idw_power=float(idw_power), smoothing=float(smoothing))
+    kw = dict(method=method, k=int(k), idw_power=float(idw_power), smoothing=float(smoothing), rbf_kernel=rbf_kernel)
     if return_knn:
         out, kd, ki = eng.interpolate(ax[0], ax[1], ax[2], mask=m, out_dtype=tdt, return_knn=True, **kw)
         host = out.cpu().numpy()
@@ -138,7 +139,8 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
 
 
 def _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,
-                           idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn):
+                           idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn,
+                           rbf_kernel="thin_plate_spline"):
     """interpolate_field for a grid_tuple that is not a rectilinear meshgrid: the (X, Y, Z) arrays are
     treated as arbitrary query points (what the reference does with every grid, interpolator.py:93)."""
     import torch
@@ -164,7 +166,8 @@ def _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbor
         qt = torch.from_numpy(np.ascontiguousarray(q)).to(dev)
         qe.build(qt, qt)
         res = eng.interpolate_points(qe, method=method, k=int(k), idw_power=float(idw_power),
-                                     smoothing=float(smoothing), out_dtype=tdt, return_knn=return_knn)
+                                     smoothing=float(smoothing), out_dtype=tdt, return_knn=return_knn,
+                                     rbf_kernel=rbf_kernel)
         out = res[0] if return_knn else res
         flat = full.reshape(3, -1)
         if sel is None:

@@ -361,6 +361,10 @@ def test_host_cabi_entry_point():
 @pytest.mark.parametrize("name,kw", [("rbf_k20", dict(method="rbf")),
                                      ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1)),
                                      ("rbf_k40", dict(method="rbf", rbf_neighbors=40)),
+                                     ("rbf_cubic_k20", dict(method="rbf", rbf_kernel="cubic")),
+                                     ("rbf_linear_k15_s005", dict(method="rbf", rbf_kernel="linear", rbf_neighbors=15,
+                                                                  smoothing=0.05)),
+                                     ("rbf_quintic_k30", dict(method="rbf", rbf_kernel="quintic", rbf_neighbors=30)),
                                      ("rbf_k60_s001", dict(method="rbf", rbf_neighbors=60, smoothing=0.01))])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_golden_rbf(case_a, name, kw, dtype):
@@ -407,6 +411,12 @@ def test_rbf_sphere_pack_vs_oracle_and_errors():
         gi.interpolate_field(_df(pts[:3], vals[:3]), grid, method="rbf")
     with pytest.raises(ValueError):  # documented limit of the CUDA path
         gi.interpolate_field(_df(pts, vals), grid, method="rbf", rbf_neighbors=61)
+    with pytest.raises(ValueError, match="epsilon"):  # RBFInterpolator: gaussian needs epsilon, the reference passes none
+        gi.interpolate_field(_df(pts, vals), grid, method="rbf", rbf_kernel="gaussian")
+    with pytest.raises(ValueError, match="must be one of"):
+        gi.interpolate_field(_df(pts, vals), grid, method="rbf", rbf_kernel="bogus")
+    with pytest.raises(ValueError, match="At least 10 data points"):
+        gi.interpolate_field(_df(pts[:9], vals[:9]), grid, method="rbf", rbf_kernel="quintic")
 
 
 # ------------------------------------------------------------------ BASELINE-size checks (c2 / c3 geometry)

@@ -46,6 +46,9 @@ def test_knn_matches_ckdtree_and_bruteforce(golden_dir, k):
     ("rbf_k20", dict(method="rbf")),
     ("rbf_k12_s01", dict(method="rbf", rbf_neighbors=12, smoothing=0.1)),
     ("rbf_k40", dict(method="rbf", rbf_neighbors=40)),
+    ("rbf_cubic_k20", dict(method="rbf", rbf_kernel="cubic")),
+    ("rbf_linear_k15_s005", dict(method="rbf", rbf_kernel="linear", rbf_neighbors=15, smoothing=0.05)),
+    ("rbf_quintic_k30", dict(method="rbf", rbf_kernel="quintic", rbf_neighbors=30)),
     ("rbf_k60_s001", dict(method="rbf", rbf_neighbors=60, smoothing=0.01)),
     ("nearest", dict(method="nearest")),
 ])
