@@ -250,7 +250,10 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   const bool sib = p.method == PTV_METHOD_SIBSON;
   const bool p2 = p.power == 2.0;
   double wsum = 0.0, su = 0.0, sv = 0.0, sw = 0.0;  // idw accumulators
-  double dsum = 0.0, ksum = 0.0;                    // sibson moments: sum d, sum d^2
+  // sibson moments about a shift close to the distances themselves (the crossing-bin edge): the
+  // one-pass variance E[(d-s)^2] - E[d-s]^2 then cancels only a few digits even when std << mean
+  double dsum = 0.0, ksum = 0.0;
+  const double dshift = sqrt(e_lo);
   // float32 output: the weight only needs float32 accuracy (relative 6e-8, far inside the 1e-5 bar),
   // so the reciprocal runs on the SFU; float64 output keeps the IEEE division.
   auto idw_weight = [&](double d2) -> double {
@@ -298,8 +301,9 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
         if (d2 < e_lo) {
           ++n_in;
           if (sib) {
-            dsum += sqrt(d2);
-            ksum += d2;
+            const double dd = sqrt(d2) - dshift;
+            dsum += dd;
+            ksum += dd * dd;
           } else {
             const double wgt = idw_weight(d2);
             const ValT val = stage_val[j];
@@ -345,8 +349,9 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
         lidx[i * T] = bi;
       }
       if (sib) {
-        dsum += sqrt(bk);
-        ksum += bk;
+        const double dd = sqrt(bk) - dshift;
+        dsum += dd;
+        ksum += dd * dd;
       } else {
         const double wgt = idw_weight(bk);
         const Value4 val = g.vals[bi];
