@@ -213,20 +213,22 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   }
 
   // ---- thresholds from the crossing bin
-  bool fail = false;
+  bool fail = false, crowded = false;
   double e_lo = 0.0, e_hi = 0.0;
+  int c_below = 0;  // particles in the bins below the crossing bin
   if (active) {
     int cum = 0, bstar = -1;
     for (int b = 0; b < kNB - 1; ++b) {
       const int h = hist[b * T];
       if (cum + h >= k) {
         bstar = b;
-        if (h > kListCap) fail = true;
+        crowded = h > kListCap;
         break;
       }
       cum += h;
     }
     if (bstar < 0) fail = true;  // crossing in the open-ended last bin
+    c_below = cum;
     e_lo = bstar * binw;
     e_hi = (bstar + 1) * binw;
     // the crossing bin must lie inside the scanned radius unless the whole grid was scanned
@@ -235,6 +237,51 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const K
   if (__syncthreads_or(fail ? 1 : 0)) {
     push_fail(3);
     return;
+  }
+  // ---- phase A2 (rare): a crossing bin that holds more particles than the short list -- typical for
+  //      voxels far from every particle, whose neighbours all sit at nearly the same distance -- is
+  //      re-histogrammed with kNB sub-bins; phase B still verifies the result exactly.
+  if (__syncthreads_or(crowded ? 1 : 0)) {
+#pragma unroll
+    for (int b = 0; b < kNB; ++b) hist[b * T] = 0;
+    const float lo32 = (float)e_lo, inv_w2 = (float)((double)kNB / binw);
+    scan_shell_pipe<T, 0>(g, tg, rg, rg, false, pbuf, seg_start, seg_off, warp_tot, cx, cy, cz,
+                          [&](const PipeBuf& pb, int m) {
+      if (active && crowded) {
+        const float4* stage32 = pb.stage32;
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+          const float4 c = stage32[j];
+          const float dx = qfx - c.x, dy = qfy - c.y, dz = qfz - c.z;
+          const float rel = (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) - lo32) * inv_w2;
+          if (rel >= 0.0f && rel < (float)kNB) hist[__float2int_rz(rel) * T] += 1;
+        }
+      }
+    });
+    if (active && crowded) {
+      const double w2 = binw / kNB;
+      int cum = c_below, b2 = -1;
+      for (int b = 0; b < kNB; ++b) {
+        const int h = hist[b * T];
+        if (cum + h >= k) {
+          b2 = b;
+          if (h > kListCap) fail = true;  // still crowded (ties / coincident particles): exact kernel
+          break;
+        }
+        cum += h;
+      }
+      if (b2 < 0) {
+        fail = true;
+      } else {  // one sub-bin of slack on each side absorbs float32 fuzz at this resolution
+        const double lo2 = e_lo + (double)max(b2 - 1, 0) * w2, hi2 = fmin(e_lo + (double)(b2 + 2) * w2, e_hi);
+        e_lo = lo2;
+        e_hi = hi2;
+      }
+    }
+    if (__syncthreads_or(fail ? 1 : 0)) {
+      push_fail(3);
+      return;
+    }
   }
 
   // ---- phase B: exact classification of the final region
