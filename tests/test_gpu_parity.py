@@ -717,3 +717,62 @@ def test_degenerate_grids_and_clouds(res):
     U, V, W = gi.interpolate_field(_df(same, vals), grid, method="idw", idw_neighbors=10, out_dtype=np.float64)
     # ten lowest-index particles, all at the same distance: plain mean of their values
     assert np.allclose(U, vals[:10, 0].mean(), rtol=1e-12) and np.allclose(W, vals[:10, 2].mean(), rtol=1e-12)
+
+
+def test_main_py_flow_steps_4_to_7():
+    """The sequence main.py:140-218 runs -- crop, outlier filter, grid, mask resampling (downscale 2),
+    no-slip boundary particles, interpolation, solid zeroing, projection cleaning -- through the drop-in
+    modules, against the same sequence through the oracle port."""
+    import types
+    from ptv_interpolation_b200 import filtering as gf
+    rng = np.random.default_rng(77)
+    nraw = 32
+    zz, yy, xx = np.meshgrid(*(np.arange(nraw, dtype=float),) * 3, indexing="ij")
+    mask_raw = np.ones((nraw,) * 3, bool)
+    for cx, cy, cz, r in ((9, 10, 11, 6.0), (22, 20, 9, 5.0), (15, 24, 23, 6.5)):
+        mask_raw &= ((xx - cx) ** 2 + (yy - cy) ** 2 + (zz - cz) ** 2) > r * r
+    bounds = ((0, nraw), (0, nraw), (0, nraw))
+    p = rng.uniform(-1, nraw + 1, size=(9000, 3)).astype(np.float32).astype(np.float64)
+    inside = mask_raw[np.clip(np.rint(p[:, 2]).astype(int), 0, nraw - 1), np.clip(np.rint(p[:, 1]).astype(int), 0, nraw - 1),
+                      np.clip(np.rint(p[:, 0]).astype(int), 0, nraw - 1)]
+    p = p[inside]
+    v = np.stack([0.2 * np.sin(0.3 * p[:, 1]), 0.1 * np.cos(0.2 * p[:, 0]), 1.0 + 0.05 * p[:, 2]], -1)
+    v[rng.choice(len(v), 40, replace=False)] *= 6.0  # outliers for the filter
+    df = _df(p, v)
+    (xmin, xmax), (ymin, ymax), (zmin, zmax) = bounds
+    df = df[(df.x >= xmin) & (df.x < xmax) & (df.y >= ymin) & (df.y < ymax) & (df.z >= zmin) & (df.z < zmax)].reset_index(drop=True)
+    args = types.SimpleNamespace(filter_outliers=True, filter_max_speed=10.0, filter_neighbors=25, filter_threshold=3.0)
+
+    def flow(mod_i, mod_p, filt):
+        d = filt(df)
+        res = int(round(nraw / 2))
+        (X, Y, Z), (x, y, z) = mod_i.create_grid(bounds, res)
+        mask = mod_i.sample_mask_on_grid(mask_raw, (X, Y, Z), bounds)
+        bx, by, bz = mod_i.extract_boundary_particles(mask_raw, bounds, sampling_step=3, thickness=2)
+        import pandas as pd
+        bdf = pd.DataFrame({"x": bx, "y": by, "z": bz, "u": np.zeros_like(bx), "v": np.zeros_like(by), "w": np.zeros_like(bz)})
+        d = pd.concat([d, bdf], ignore_index=True)
+        return d, (X, Y, Z), (x, y, z), mask
+
+    d_g, grid_g, ax_g, mask_g = flow(gi, gp, lambda d: gf.apply_filters(d, args))
+    keep, _ = rp.outlier_keep_mask(df[["x", "y", "z"]].values, df[["u", "v", "w"]].values, 25, 3.0)
+
+    class _RefI:  # the oracle port behind interpolator.py's names
+        create_grid = staticmethod(rp.create_grid)
+        sample_mask_on_grid = staticmethod(rp.sample_mask_on_grid)
+        extract_boundary_particles = staticmethod(rp.extract_boundary_particles)
+    d_r, grid_r, ax_r, mask_r = flow(_RefI, None, lambda d: d[keep].reset_index(drop=True))
+    assert np.array_equal(d_g.values, d_r.values) and np.array_equal(mask_g, mask_r)
+    U, V, W = gi.interpolate_field(d_g, grid_g, method="idw", idw_neighbors=50, idw_power=2.0, out_dtype=np.float64)
+    U[~mask_g] = 0; V[~mask_g] = 0; W[~mask_g] = 0  # main.py:202-207 mutates the returned arrays in place
+    Ur, Vr, Wr = rp.interpolate_field(d_r[["x", "y", "z"]].values, d_r[["u", "v", "w"]].values, grid_r, method="idw")
+    Ur, Vr, Wr = rp.apply_mask_zero(Ur, Vr, Wr, mask_r)
+    _assert_vel(np.stack([U, V, W]), np.stack([Ur, Vr, Wr]), d_r[["u", "v", "w"]].values)
+    # the masked call gives the same field without the caller's zeroing
+    Um, Vm, Wm = gi.interpolate_field(d_g, grid_g, method="idw", mask=mask_g, out_dtype=np.float64)
+    assert np.abs(Um - U).max() <= 1e-11 and np.abs(Wm - W).max() <= 1e-11
+    dx, dy, dz = (float(a[1] - a[0]) for a in ax_g)
+    uc, vc, wc = gp.clean_divergence(U, V, W, mask_g, dx, dy, dz, iterations=2)
+    ucr, vcr, wcr = rp.clean_divergence_projection(Ur, Vr, Wr, mask_r, dx, dy, dz, iterations=2)
+    for a, b in ((uc, ucr), (vc, vcr), (wc, wcr)):
+        assert np.abs(a - b).max() <= 1e-6
