@@ -237,7 +237,7 @@ __device__ __forceinline__ int scan_shell(const HashGrid& g, const TileGeom& tg,
 // Two staging buffers; the records (and values) of chunk c+1 travel global -> shared with cp.async
 // (LDGSTS, no registers) while chunk c is being scanned, so the global-memory latency of staging is
 // hidden and each chunk costs one block barrier instead of two.
-static constexpr int kPipeCap = 128;  // records per pipelined chunk
+static constexpr int kPipeCap = 64;  // records per pipelined chunk
 
 struct PipeBuf {
   ParticleRec* stage64;  // [kPipeCap]

@@ -31,7 +31,7 @@ static constexpr int kNB = 96;        // histogram bins over [0, Tmax), 16-bit c
 static constexpr int kListCap = 16;   // capacity of the crossing-bin list
 static constexpr int kMinEstimate = 16;
 static constexpr int kVPT = 8;  // voxels of the region examined per thread (region = kVPT * T voxels)
-static_assert(kPipeCap == 128, "the exact passes use two 64-bit accept masks per chunk");
+static_assert(kPipeCap <= 128, "the exact passes use two 64-bit accept masks per chunk");
 
 // Values staged next to the candidates: float32 when the output is float32 (rounding 6e-8 relative,
 // far inside the 1e-5 bar), float64 when the caller asked for float64 output.
@@ -52,7 +52,7 @@ template <> struct StageVal<double> {
 };
 
 template <int T, int TX, int TY, int TZ, typename OutT>
-__global__ void __launch_bounds__(T, T == 128 ? 5 : 8) knn_stream_kernel(const KnnParams p) {
+__global__ void __launch_bounds__(T, T == 128 ? 6 : 8) knn_stream_kernel(const KnnParams p) {
   static_assert(TX * TY * TZ == T, "tile shape");
   constexpr int NW = T / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
