@@ -36,6 +36,7 @@ extern "C" {
 #define PTV_ERR_CUDA 3
 #define PTV_ERR_SINGULAR 4
 #define PTV_ERR_NOMEM 5
+#define PTV_ERR_QHULL 6 /* method='linear': what scipy.spatial.QhullError reports (too few points) */
 
 /* interpolation methods (interpolator.py:65 `method=`) */
 #define PTV_METHOD_IDW 0     /* interpolator.py:126-155 */
@@ -48,6 +49,11 @@ extern "C" {
 #define PTV_METHOD_RBF_CUBIC 5
 #define PTV_METHOD_RBF_LINEAR 6
 #define PTV_METHOD_RBF_QUINTIC 7
+/* interpolator.py:197 griddata(method='linear', fill_value=0.0): barycentric weights in the Delaunay
+ * tetrahedron that holds the voxel, 0 outside the convex hull.  k is ignored; the optional lists hold 4
+ * entries per voxel: the tetrahedron's vertex rows in ascending order (-1 outside the hull) in knn_idx and
+ * their barycentric weights in knn_dist. */
+#define PTV_METHOD_LINEAR 8
 
 /* output element types for the velocity grids */
 #define PTV_F32 0
@@ -117,6 +123,11 @@ int ptv_knn_stats(const ptv_hash* h, int64_t* used_stream, int64_t* tiles_failed
  * neighbour beyond the histogram range, [2] crossing bin larger than the short list, [3] exact
  * verification failed. */
 int ptv_knn_fail_reasons(const ptv_hash* h, int64_t reasons[4]);
+/* With tuning "stats" = 1, after a PTV_METHOD_LINEAR call: [0] voxels finished on the warp-shared candidate
+ * set, [1] of those, voxels that re-used the previous voxel's tetrahedron, [2] voxels solved on their own
+ * (growing region), [3] candidate sets read from global memory, [4] voxels outside the convex hull,
+ * [5] unresolved voxels (pivot limit; written as 0), [6] pivots, [7] size of the hull-candidate list. */
+int ptv_linear_stats(const ptv_hash* h, int64_t stats[8]);
 
 /* ---- mask resampling: replaces sample_mask_on_grid (interpolator.py:205-238).  The
  *      per-axis nearest index maps (-1 == out of bounds) are computed by the host shim with

@@ -197,8 +197,55 @@ def main():
                         u3=uc, v3=vc, w3=wc, u1=u1, v1=v1, w1=w1, lap_x=xt, lap_Ax=A @ xt,
                         div0=rp.compute_consistent_divergence(uh, vh, wh, mh, *hh),
                         div3=rp.compute_consistent_divergence(uc, vc, wc, mh, *hh))
+    gen_linear(ri)
     print("golden vectors written to", os.path.normpath(OUT))
 
 
+def _simplex_rows(pts, fc):
+    """Vertex rows (ascending) of the Delaunay tetrahedron scipy finds for each query, -1 outside the hull."""
+    from scipy.spatial import Delaunay
+    tri = Delaunay(pts)
+    s = tri.find_simplex(fc)
+    rows = np.where(s[:, None] >= 0, np.sort(tri.simplices[np.maximum(s, 0)], axis=1), -1)
+    return rows.astype(np.int64)
+
+
+def gen_linear(ri):
+    """case I: method='linear' (interpolator.py:197 -> griddata -> Qhull Delaunay), the reference's default.
+    `python oracle/gen_golden.py linear` writes only this file."""
+    out = {}
+    # I1: case A's cloud and grid (all voxels well inside the hull)
+    rng = np.random.default_rng(101)
+    bounds = ((0, 14), (0, 12), (0, 10))
+    res = (13, 11, 9)
+    pts = f32r(rng.uniform([-1, -1, -1], [15, 13, 11], size=(600, 3)))
+    vals = f32r(rng.normal(size=(600, 3)))
+    grid, _ = ri.create_grid(bounds, res)
+    fc = np.stack([grid[0].ravel(), grid[1].ravel(), grid[2].ravel()], -1)
+    U, V, W = ri.interpolate_field(make_df(pts, vals), grid, method="linear")
+    out.update(a_points=pts, a_values=vals, a_bounds=np.array(bounds, dtype=np.float64), a_res=np.array(res),
+               a_uvw=np.stack([U, V, W], 0), a_simplex=_simplex_rows(pts, fc))
+    # I2: a cloud smaller than the grid: a third of the voxels lie outside the convex hull (fill_value 0)
+    rng = np.random.default_rng(909)
+    pts = f32r(rng.uniform(2.5, 9.5, size=(400, 3)))
+    vals = f32r(np.stack([1.0 + 0.2 * pts[:, 1], np.sin(pts[:, 0]), 0.1 * pts[:, 2] ** 2], -1))
+    bounds = ((0, 13), (0, 13), (0, 13))
+    grid, _ = ri.create_grid(bounds, (14, 12, 10))
+    fc = np.stack([grid[0].ravel(), grid[1].ravel(), grid[2].ravel()], -1)
+    U, V, W = ri.interpolate_field(make_df(pts, vals), grid, method="linear")
+    out.update(b_points=pts, b_values=vals, b_bounds=np.array(bounds, dtype=np.float64), b_res=np.array((14, 12, 10)),
+               b_uvw=np.stack([U, V, W], 0), b_simplex=_simplex_rows(pts, fc))
+    # I3: case B's cloud: random pore particles + zero-velocity wall particles on the voxel lattice
+    # (co-spherical by construction; the grid points coincide with lattice sites) -- values only
+    cb = np.load(os.path.join(OUT, "case_b_boundary.npz"))
+    gridb, _ = ri.create_grid(((0, 12), (0, 12), (0, 12)), 12)
+    U, V, W = ri.interpolate_field(make_df(cb["points"], cb["values"]), gridb, method="linear")
+    out.update(c_uvw=np.stack([U, V, W], 0))
+    np.savez_compressed(os.path.join(OUT, "case_i_linear.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["linear"]:
+        gen_linear(load_reference()[0])
+    else:
+        main()

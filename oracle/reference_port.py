@@ -27,6 +27,7 @@ __all__ = [
     "extract_boundary_particles", "compute_consistent_divergence", "flux_xy", "flux_xz",
     "flux_yz", "mid_plane_x_flux", "mean_abs_div", "apply_mask_zero", "outlier_keep_mask", "compute_strain_rate", "compute_vorticity",
     "build_laplacian_matrix", "apply_consistent_correction", "clean_divergence_projection",
+    "delaunay_simplex_rows",
 ]
 
 
@@ -187,6 +188,14 @@ def interpolate_field(points, values, grid_tuple, method="idw", rbf_neighbors=20
         # interpolator.py:197 griddata(method='nearest') == cKDTree k=1 lookup
         dist, idx, _ = knn_canonical(points, fc, 1, workers=workers)
         out[:] = values[idx[:, 0]]
+    elif method == "linear":
+        # interpolator.py:197 griddata(points, values, grid, method='linear', fill_value=0.0)
+        # == scipy LinearNDInterpolator (Qhull Delaunay, find_simplex, barycentric weights).  An
+        # independent restatement without SciPy is oracle/delaunay_lp.py.
+        from scipy.interpolate import LinearNDInterpolator
+        interp = LinearNDInterpolator(points, values, fill_value=0.0)
+        for s in range(0, nq, chunk_voxels):
+            out[s:s + chunk_voxels] = interp(fc[s:s + chunk_voxels])
     else:
         raise NotImplementedError(method)
     interp3 = out.reshape(X.shape + (3,))
@@ -194,6 +203,28 @@ def interpolate_field(points, values, grid_tuple, method="idw", rbf_neighbors=20
     if return_knn and method in ("idw", "sibson"):
         return U, V, W, np.concatenate(keep_d), np.concatenate(keep_i)
     return U, V, W
+
+
+def delaunay_simplex_rows(points, queries):
+    """Vertex rows (ascending) of the tetrahedron ``scipy.spatial.Delaunay(points).find_simplex`` returns
+    for each query and the barycentric weights in that order; rows are -1 outside the convex hull.
+    This is the simplex LinearNDInterpolator evaluates in (interpolator.py:197)."""
+    from scipy.spatial import Delaunay
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    queries = np.ascontiguousarray(queries, dtype=np.float64)
+    tri = Delaunay(points)
+    s = tri.find_simplex(queries)
+    ok = s >= 0
+    simp = tri.simplices[np.maximum(s, 0)]
+    T = tri.transform[np.maximum(s, 0)]
+    b3 = np.einsum("nij,nj->ni", T[:, :3, :], queries - T[:, 3, :])
+    b = np.concatenate([b3, 1.0 - b3.sum(1, keepdims=True)], axis=1)
+    order = np.argsort(simp, axis=1)
+    rows = np.take_along_axis(simp, order, 1).astype(np.int64)
+    b = np.take_along_axis(b, order, 1)
+    rows[~ok] = -1
+    b[~ok] = np.nan
+    return rows, b
 
 
 def apply_mask_zero(U, V, W, mask):

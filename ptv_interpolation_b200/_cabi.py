@@ -11,9 +11,10 @@ import os
 
 import numpy as np
 
-PTV_OK, PTV_ERR_INVALID, PTV_ERR_TOO_FEW, PTV_ERR_CUDA, PTV_ERR_SINGULAR, PTV_ERR_NOMEM = range(6)
+PTV_OK, PTV_ERR_INVALID, PTV_ERR_TOO_FEW, PTV_ERR_CUDA, PTV_ERR_SINGULAR, PTV_ERR_NOMEM, PTV_ERR_QHULL = range(7)
 METHOD_IDW, METHOD_SIBSON, METHOD_NEAREST, METHOD_RBF, METHOD_MADFILTER = range(5)
 METHOD_RBF_CUBIC, METHOD_RBF_LINEAR, METHOD_RBF_QUINTIC = 5, 6, 7
+METHOD_LINEAR = 8  # griddata(method='linear'): Delaunay tetrahedron + barycentric weights
 F32, F64 = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -22,7 +23,7 @@ _lib = None
 
 EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
-    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_points", "ptv_outlier_filter",
+    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_linear_stats", "ptv_knn_points", "ptv_outlier_filter",
     "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_strain_vorticity", "ptv_poisson_workspace_bytes", "ptv_poisson_lsqr", "ptv_projection_correct",
     "ptv_interpolate_host",
@@ -66,6 +67,8 @@ def _declare(lib):
     lib.ptv_knn_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.ptv_knn_fail_reasons.restype = i32
     lib.ptv_knn_fail_reasons.argtypes = [vp, C.POINTER(i64 * 4)]
+    lib.ptv_linear_stats.restype = i32
+    lib.ptv_linear_stats.argtypes = [vp, C.POINTER(i64 * 8)]
     lib.ptv_mask_gather.restype = i32
     lib.ptv_mask_gather.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
     lib.ptv_boundary_voxels.restype = i32
@@ -120,4 +123,10 @@ def check(rc: int):
         raise np.linalg.LinAlgError(msg)
     if rc == PTV_ERR_NOMEM:
         raise MemoryError(msg)
+    if rc == PTV_ERR_QHULL:
+        try:  # what griddata raises from Qhull (a RuntimeError subclass)
+            from scipy.spatial import QhullError
+        except Exception:  # pragma: no cover
+            QhullError = RuntimeError
+        raise QhullError(msg)
     raise PTVError(msg)

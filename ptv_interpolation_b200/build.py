@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptvb200.so")
-SOURCES = ["cabi.cu", "hash_build.cu", "knn_interp.cu", "knn_stream.cu", "knn_dispatch.cu", "grid_ops.cu", "stencil_fused.cu", "projection.cu"]
+SOURCES = ["cabi.cu", "hash_build.cu", "knn_interp.cu", "knn_stream.cu", "knn_dispatch.cu", "delaunay_linear.cu", "grid_ops.cu", "stencil_fused.cu", "projection.cu"]
 HEADERS = [os.path.join(CSRC, "ptv_internal.cuh"), os.path.join(CSRC, "knn_common.cuh"), os.path.join(ROOT, "include", "ptv_b200.h")]
 
 

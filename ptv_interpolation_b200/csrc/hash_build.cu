@@ -372,6 +372,8 @@ extern "C" int ptv_hash_destroy(ptv_hash* h) {
   cudaFree(h->err_flag);
   cudaFree(h->fail_list);
   cudaFree(h->fail_count);
+  cudaFree(h->hull_rec);
+  cudaFree(h->hull_tab);
   if (h->bbox_host) cudaFreeHost(h->bbox_host);
   if (h->err_host) cudaFreeHost(h->err_host);
   delete h;
@@ -385,6 +387,7 @@ extern "C" int ptv_hash_build(ptv_hash* h, const double* d_points, const double*
   if (n >= (int64_t)2147483000) { set_error("ptv_hash_build: more than 2^31 particles"); return PTV_ERR_INVALID; }
   cudaStream_t stream = (cudaStream_t)stream_;
   h->built = false;
+  h->hull_valid = false;
 
   // 1. bounding box (and finiteness) of the cloud
   double* partial = h->bbox_dev + 8;

@@ -44,6 +44,9 @@ struct KnnParams {
   uint8_t* keep;
   double* kth_dist;
   double mad_threshold;
+  // method='linear' (delaunay_linear.cu): particles that may be convex-hull vertices (NULL = scan all)
+  const ParticleRec* hull_rec;
+  int hull_n;
 };
 
 __device__ __forceinline__ bool key_greater(double ka, int ia, double kb, int ib) {
@@ -403,5 +406,7 @@ __device__ __forceinline__ double estimate_radius(const HashGrid& g, const TileG
 int launch_knn_heap(KnnParams& p, int T, bool f32, cudaStream_t stream);
 int launch_knn_stream(KnnParams& p, int T, bool f32, cudaStream_t stream);
 size_t knn_heap_smem_bytes(int T, int k, int method);
+int launch_delaunay_linear(KnnParams& p, bool f32, cudaStream_t stream);
+int ensure_hull_list(ptv_hash* h, cudaStream_t stream);
 
 }  // namespace ptv

@@ -47,6 +47,31 @@ static int rbf_check(int64_t n_particles, int& k, int npoly, int degree, double 
   return PTV_OK;
 }
 
+// griddata(method='linear') needs a non-degenerate triangulation: Qhull wants at least 5 points in 3-D
+static int linear_check(int64_t n) {
+  if (n < 5) {
+    set_error("QH6214 qhull input error: not enough points(" + std::to_string(n) + ") to construct initial simplex (need 5)");
+    return PTV_ERR_QHULL;
+  }
+  return PTV_OK;
+}
+
+// method='linear': hull-candidate list (once per hash build), statistics slots, one launch
+static int run_linear(ptv_hash* h, KnnParams& p, bool f32, cudaStream_t stream) {
+  int rc = ensure_fail_buffers(h, 0);
+  if (rc != PTV_OK) return rc;
+  PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, 8 * sizeof(unsigned long long), stream));
+  p.stats = tuning().stats != 0 ? h->fail_count + 1 : nullptr;
+  if (tuning().hull != 0) {
+    rc = ensure_hull_list(h, stream);
+    if (rc != PTV_OK) return rc;
+    p.hull_rec = h->hull_rec;
+    p.hull_n = h->hull_n;
+  }
+  h->last_used_stream = false;
+  return launch_delaunay_linear(p, f32, stream);
+}
+
 static void tile_shape(int T, int& tx, int& ty, int& tz) {
   tx = T == 128 ? 8 : 4; ty = 4; tz = T == 32 ? 2 : 4;
 }
@@ -61,9 +86,15 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_knn_interp: empty grid"); return PTV_ERR_INVALID; }
   if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_interp: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
   if (method == PTV_METHOD_NEAREST) k = 1;
+  if (method == PTV_METHOD_LINEAR) {
+    k = 4;
+    const int rc0 = linear_check(h->n);
+    if (rc0 != PTV_OK) return rc0;
+  }
   int rbf_kern = 0, rbf_npoly = 4, rbf_degree = 1;
   const bool is_rbf = rbf_variant(method, rbf_kern, rbf_npoly, rbf_degree);
-  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST && !is_rbf) {
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST && !is_rbf &&
+      method != PTV_METHOD_LINEAR) {
     set_error("ptv_knn_interp: unsupported method");
     return PTV_ERR_INVALID;
   }
@@ -95,7 +126,9 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.qrec = nullptr; p.nq = 0; p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
   p.tiles_x = p.tiles_y = p.tiles_z = 0;
+  p.hull_rec = nullptr; p.hull_n = 0;
   if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
+  if (method == PTV_METHOD_LINEAR) return run_linear(h, p, out_dtype == PTV_F32, stream);
 
   const size_t smem_max = 227 * 1024;
   const bool f32 = out_dtype == PTV_F32;
@@ -162,6 +195,7 @@ static void init_point_params(KnnParams& p, const ptv_hash* h, const ptv_hash* q
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.qrec = q->rec; p.nq = q->n;
   p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
+  p.hull_rec = nullptr; p.hull_n = 0;
 }
 
 static int pick_heap_tile(int k, int method) {
@@ -180,9 +214,15 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
   if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_points: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
   if (!want_uvw && !d_knn_idx) { set_error("ptv_knn_points: nothing to compute"); return PTV_ERR_INVALID; }
   if (method == PTV_METHOD_NEAREST) k = 1;
+  if (method == PTV_METHOD_LINEAR) {
+    k = 4;
+    const int rc0 = linear_check(h->n);
+    if (rc0 != PTV_OK) return rc0;
+  }
   int rbf_kern = 0, rbf_npoly = 4, rbf_degree = 1;
   const bool is_rbf = rbf_variant(method, rbf_kern, rbf_npoly, rbf_degree);
-  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST && !is_rbf) {
+  if (method != PTV_METHOD_IDW && method != PTV_METHOD_SIBSON && method != PTV_METHOD_NEAREST && !is_rbf &&
+      method != PTV_METHOD_LINEAR) {
     set_error("ptv_knn_points: unsupported method");
     return PTV_ERR_INVALID;
   }
@@ -209,6 +249,11 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
   }
   p.u = d_u; p.v = d_v; p.w = d_w;
   p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
+  if (method == PTV_METHOD_LINEAR) {
+    const int rcl = run_linear(const_cast<ptv_hash*>(h), p, out_dtype == PTV_F32, stream);
+    if (scratch) { cudaStreamSynchronize(stream); cudaFree(scratch); }
+    return rcl;
+  }
   const int T = pick_heap_tile(k, method);
   if (T == 0) { cudaFree(scratch); set_error("ptv_knn_points: k too large for shared memory (max ~580)"); return PTV_ERR_INVALID; }
   if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
@@ -252,6 +297,15 @@ extern "C" int ptv_knn_fail_reasons(const ptv_hash* hc, int64_t reasons[4]) {
   for (int i = 0; i < 4; ++i) reasons[i] = (int64_t)host[2 + i];
   h->last_stage_counts[0] = (int64_t)host[6];
   h->last_stage_counts[1] = (int64_t)host[7];
+  return PTV_OK;
+}
+
+extern "C" int ptv_linear_stats(const ptv_hash* h, int64_t stats[8]) {
+  if (!h || !stats) { set_error("ptv_linear_stats: NULL argument"); return PTV_ERR_INVALID; }
+  unsigned long long host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (h->fail_count != nullptr) PTV_CUDA(cudaMemcpy(host, h->fail_count, sizeof(host), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 7; ++i) stats[i] = (int64_t)host[1 + i];
+  stats[7] = h->hull_valid ? h->hull_n : 0;
   return PTV_OK;
 }
 

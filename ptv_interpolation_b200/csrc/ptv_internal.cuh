@@ -44,6 +44,7 @@ struct Tuning {
   int stream = 1;    // 1 = streaming kernel for idw/sibson with k >= 8 (heap kernel as fallback)
   int stream_tile = 128;
   int stats = 0;     // 1 = count streamed tiles
+  int hull = 1;      // method='linear': 1 = decide hull membership on the hull-candidate list, 0 = scan all particles
   double rscale = 1.3;  // stream kernel: first scan radius^2 = rscale * r_est^2
 };
 Tuning& tuning();
@@ -75,6 +76,13 @@ struct ptv_hash {
   int* fail_list = nullptr;       // tiles handed from the streaming to the heap kernel
   int64_t fail_cap = 0;
   unsigned long long* fail_count = nullptr;  // [0] low 32 bits: fail count; [1]: streamed tiles (stats)
+  // method='linear': hull-candidate records and the dominance tables they come from (built on demand)
+  ptv::ParticleRec* hull_rec = nullptr;
+  int64_t hull_cap = 0;
+  int* hull_tab = nullptr;
+  int hull_cap_rows = 0;
+  int hull_n = 0;
+  bool hull_valid = false;
   bool last_used_stream = false;
   int64_t last_stage_counts[2] = {0, 0};
   int64_t cap_n = 0;

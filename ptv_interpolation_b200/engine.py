@@ -14,7 +14,7 @@ import torch
 from . import _cabi
 
 _METHODS = {"idw": _cabi.METHOD_IDW, "sibson": _cabi.METHOD_SIBSON, "nearest": _cabi.METHOD_NEAREST,
-            "rbf": _cabi.METHOD_RBF}
+            "rbf": _cabi.METHOD_RBF, "linear": _cabi.METHOD_LINEAR}
 # scipy.interpolate.RBFInterpolator kernels usable without `epsilon` (the reference never passes one)
 _RBF_KERNELS = {"thin_plate_spline": _cabi.METHOD_RBF, "cubic": _cabi.METHOD_RBF_CUBIC,
                 "linear": _cabi.METHOD_RBF_LINEAR, "quintic": _cabi.METHOD_RBF_QUINTIC}
@@ -132,6 +132,8 @@ class PTVEngine:
             raise ValueError("out must be a (3, nz, ny, nx) tensor whose components are contiguous")
         if method == "nearest":
             k = 1
+        if method == "linear":
+            k = 4  # the lists hold the tetrahedron's vertex rows and barycentric weights
         kd = ki = None
         if return_knn:
             ki = torch.empty((nz * ny * nx, k), dtype=torch.int64, device=self.device)
@@ -184,6 +186,8 @@ class PTVEngine:
         nq = queries.n_particles
         if method == "nearest":
             k = 1
+        if method == "linear":
+            k = 4
         out = torch.empty((3, nq), dtype=out_dtype, device=self.device) if values else None
         kd = ki = None
         if return_knn:
@@ -218,6 +222,14 @@ class PTVEngine:
         _cabi.check(self.lib.ptv_knn_fail_reasons(self._h, C.byref(r)))
         return {"used_stream": bool(a.value), "tiles_failed": b.value, "tiles_streamed": c.value,
                 "fail_reasons": {"no_estimate": r[0], "beyond_range": r[1], "bin_overflow": r[2], "verify": r[3]}}
+
+    def linear_stats(self):
+        """Diagnostics of the last method='linear' call (needs set_tuning(stats=1))."""
+        r = (C.c_int64 * 8)()
+        _cabi.check(self.lib.ptv_linear_stats(self._h, C.byref(r)))
+        keys = ("shared_pass", "reused_tetrahedra", "general_path", "global_candidate_sets", "outside_hull",
+                "unresolved", "pivots", "hull_candidates")
+        return dict(zip(keys, (int(v) for v in r)))
 
     # ------------------------------------------------------------------ grid ops
     def mask_gather(self, mask_raw, ix, iy, iz):

@@ -23,7 +23,7 @@ from .engine import default_engine
 __all__ = ["load_ptv_data", "load_mask", "create_grid", "interpolate_field", "sample_mask_on_grid",
            "extract_boundary_particles"]
 
-_GPU_METHODS = ("idw", "sibson", "nearest", "rbf")
+_GPU_METHODS = ("linear", "idw", "sibson", "nearest", "rbf")
 
 
 def load_ptv_data(filepath):
@@ -101,9 +101,8 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     points = df[["x", "y", "z"]].values
     values = df[["u", "v", "w"]].values
     if method not in _GPU_METHODS:
-        raise NotImplementedError(
-            f"method={method!r} (scipy griddata / Delaunay, interpolator.py:197) is not implemented on the "
-            f"CUDA path; supported methods: {_GPU_METHODS}")
+        # interpolator.py:197 hands every other name to griddata, which knows 'cubic' only in 1-D / 2-D
+        raise ValueError(f"Unknown interpolation method {method!r} for 3 dimensional data")
     if method == "rbf":
         from .engine import method_code
         method_code("rbf", rbf_kernel)  # RBFInterpolator's kernel / epsilon checks (ValueError)
@@ -116,7 +115,7 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     x, y, z = axes
     pts = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev)
     vals = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
-    k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors}[method]
+    k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors, "linear": 4}[method]
     if method == "rbf":
         k = min(int(k), len(points))  # scipy _rbfinterp.py:313 clamps silently
     eng.build(pts, vals)
@@ -153,7 +152,7 @@ def _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbor
     if mask is not None:
         sel = np.flatnonzero(np.asarray(mask).ravel() != 0)
         q = q[sel]
-    k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors}[method]
+    k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors, "linear": 4}[method]
     if method == "rbf":
         k = min(int(k), len(points))
     tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64

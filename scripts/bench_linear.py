@@ -1,0 +1,37 @@
+"""Timings of method='linear' (Delaunay tetrahedron + barycentric weights, csrc/delaunay_linear.cu) on one
+GPU -> JSON line.  Usage: python scripts/bench_linear.py [c1 c2 c3 c4]"""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from ptv_interpolation_b200 import synthetic
+from ptv_interpolation_b200.engine import PTVEngine, set_tuning
+
+dev = torch.device("cuda", 0)
+eng = PTVEngine(dev)
+out = {}
+set_tuning(stats=1)
+for name in (sys.argv[1:] or ["c1", "c2"]):
+    cfg = synthetic.make_config(name, device=dev)
+    n = cfg["n"]
+    ax = torch.linspace(0, n - 1, n, dtype=torch.float64, device=dev)
+    mask = cfg["mask"].view(torch.uint8)
+    eng.build(cfg["points"], cfg["values"])
+    res = torch.empty((3, n, n, n), dtype=torch.float32, device=dev)
+    best = 1e30
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.interpolate(ax, ax, ax, mask=mask, method="linear", out=res)
+        e1.record()
+        torch.cuda.synchronize()
+        if rep:
+            best = min(best, e0.elapsed_time(e1))
+    pore = int(cfg["mask"].sum())
+    out[f"linear_{name}"] = {"grid": n, "particles": int(cfg["points"].shape[0]), "pore_voxels": pore, "ms": best,
+                             "pore_voxels_per_s": pore / best * 1e3, "stats": eng.linear_stats()}
+    print(name, out[f"linear_{name}"], file=sys.stderr, flush=True)
+    del cfg, mask, res
+print(json.dumps(out))

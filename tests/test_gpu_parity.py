@@ -328,8 +328,8 @@ def test_known_answers_and_errors():
     bad[3, 1] = np.nan
     with pytest.raises(ValueError):
         gi.interpolate_field(_df(bad, vals), grid, method="idw", idw_neighbors=10)
-    with pytest.raises(NotImplementedError):
-        gi.interpolate_field(_df(pts, vals), grid, method="linear")
+    with pytest.raises(ValueError):  # griddata knows 'cubic' only in 1-D / 2-D (interpolator.py:197)
+        gi.interpolate_field(_df(pts, vals), grid, method="cubic")
     # dense (np.meshgrid) grids as the reference builds them are accepted too
     og, _ = rp.create_grid(((0, 10), (0, 10), (0, 10)), 10)
     U2, _, _ = gi.interpolate_field(_df(pts, vals), og, method="idw", idw_neighbors=10, out_dtype=np.float64)
@@ -776,3 +776,133 @@ def test_main_py_flow_steps_4_to_7():
     ucr, vcr, wcr = rp.clean_divergence_projection(Ur, Vr, Wr, mask_r, dx, dy, dz, iterations=2)
     for a, b in ((uc, ucr), (vc, vcr), (wc, wcr)):
         assert np.abs(a - b).max() <= 1e-6
+
+
+# ------------------------------------------------------------------ N4: method='linear' (Delaunay, interpolator.py:197)
+def _linear_case(g, tag):
+    pts, vals = g[tag + "_points"], g[tag + "_values"]
+    grid, _ = gi.create_grid(_bounds(g[tag + "_bounds"]), tuple(int(r) for r in g[tag + "_res"]))
+    return pts, vals, grid
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("hull", [1, 0])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_linear_golden(golden_dir, tag, hull, dtype):
+    """The reference's default method against golden vectors of the unmodified reference: values within
+    tolerance, and the tetrahedron each voxel was evaluated in is the one scipy's Delaunay finds (vertex
+    rows bit-exact; -1 = outside the convex hull, where the reference's fill_value gives 0)."""
+    g = np.load(os.path.join(golden_dir, "case_i_linear.npz"))
+    pts, vals, grid = _linear_case(g, tag)
+    set_tuning(hull=hull, stats=1)
+    try:
+        U, V, W, bw, rows = gi.interpolate_field(_df(pts, vals), grid, method="linear", out_dtype=dtype,
+                                                 return_knn=True)
+        st = gi.default_engine().linear_stats()
+    finally:
+        set_tuning(hull=1, stats=0)
+    assert U.dtype == dtype
+    assert st["unresolved"] == 0
+    assert np.array_equal(rows, g[tag + "_simplex"])
+    _assert_vel(np.stack([U, V, W]), g[tag + "_uvw"], vals)
+    outside = g[tag + "_simplex"][:, 0] < 0
+    assert np.all(np.stack([U, V, W]).reshape(3, -1)[:, outside] == 0)
+    assert st["outside_hull"] == int(outside.sum())
+    if dtype == np.float64:
+        assert np.abs(np.stack([U, V, W]) - g[tag + "_uvw"]).max() <= 1e-11
+        inside = ~outside
+        assert np.abs(bw[inside].sum(1) - 1.0).max() <= 1e-12 and bw[inside].min() >= -1e-9
+
+
+def test_linear_lattice_wall_particles_golden(golden_dir):
+    """Pore particles + zero-velocity wall particles on the voxel lattice (main.py:173-178), grid points ON
+    lattice sites: co-spherical points make the triangulation non-unique, the interpolant is not (all
+    ambiguous tetrahedra carry zeros) -- values match the reference's Qhull result."""
+    g = np.load(os.path.join(golden_dir, "case_i_linear.npz"))
+    cb = np.load(os.path.join(golden_dir, "case_b_boundary.npz"))
+    grid, _ = gi.create_grid(((0, 12), (0, 12), (0, 12)), 12)
+    set_tuning(stats=1)
+    try:
+        U, V, W = gi.interpolate_field(_df(cb["points"], cb["values"]), grid, method="linear", out_dtype=np.float64)
+        st = gi.default_engine().linear_stats()
+    finally:
+        set_tuning(stats=0)
+    assert st["unresolved"] == 0
+    assert np.abs(np.stack([U, V, W]) - g["c_uvw"]).max() <= 1e-9
+    # with the pore mask, solid voxels are skipped and written 0 (what main.py:202-207 does next)
+    m = cb["mask_grid"]
+    Um, Vm, Wm = gi.interpolate_field(_df(cb["points"], cb["values"]), grid, method="linear", mask=m,
+                                      out_dtype=np.float64)
+    assert np.all(np.stack([Um, Vm, Wm])[:, ~m] == 0)
+    # (a different warp bounding box may pick another of the equivalent tetrahedra: same value to rounding)
+    assert np.abs(np.stack([Um, Vm, Wm])[:, m] - np.stack([U, V, W])[:, m]).max() <= 1e-11
+
+
+@pytest.mark.parametrize("hull", [1, 0])
+def test_linear_sphere_pack_vs_oracle(hull):
+    """Config-1-like sphere pack (96^3 grid, 40k vectors + lattice wall particles, pore mask): every pore
+    voxel against scipy's Delaunay (simplex rows exact, values within tolerance); linear precision: a
+    field that is linear in space is reproduced exactly inside the hull."""
+    n = 72
+    mask = synthetic.hex6_sphere_pack_mask(n)
+    p = synthetic.sample_pore_particles(mask, 30000, seed=5)
+    v = synthetic.sphere_pack_flow(p, n)
+    p, v, mask = p.numpy(), v.numpy(), mask.numpy()
+    bounds = ((0, n), (0, n), (0, n))
+    bx, by, bz = rp.extract_boundary_particles(mask, bounds, sampling_step=3, thickness=1)
+    pts = np.concatenate([p, np.stack([bx, by, bz], -1)], 0)
+    vals = np.concatenate([v, np.zeros((len(bx), 3))], 0)
+    grid, _ = gi.create_grid(bounds, n)
+    set_tuning(hull=hull, stats=1)
+    try:
+        U, V, W, bw, rows = gi.interpolate_field(_df(pts, vals), grid, method="linear", mask=mask,
+                                                 out_dtype=np.float64, return_knn=True)
+        st = gi.default_engine().linear_stats()
+    finally:
+        set_tuning(hull=1, stats=0)
+    assert st["unresolved"] == 0
+    og, _ = rp.create_grid(bounds, n)
+    fc = rp.flat_coords(og)
+    sel = np.flatnonzero(mask.ravel())
+    ref_rows, ref_b = rp.delaunay_simplex_rows(pts, fc[sel])
+    same = (rows[sel] == ref_rows).all(1)
+    # the lattice wall particles are co-spherical: where Qhull and the kernel split such a cell differently
+    # (0.1 % of the voxels) the tetrahedra differ but, all ambiguous vertices carrying zeros, the values do not
+    assert same.mean() >= 0.995, float(same.mean())
+    ref = rp.interpolate_field(pts, vals, (fc[sel, 0], fc[sel, 1], fc[sel, 2]), method="linear")
+    got = np.stack([U, V, W]).reshape(3, -1)[:, sel]
+    _assert_vel(got, np.stack(ref), vals)
+    assert np.all(np.stack([U, V, W])[:, ~mask] == 0)
+    lin = np.stack([2.0 + 0.5 * pts[:, 0], -1.0 + 0.25 * pts[:, 1] - 0.1 * pts[:, 2], 0.3 * pts[:, 2]], -1)
+    Ul, Vl, Wl = gi.interpolate_field(_df(pts, lin), grid, method="linear", mask=mask, out_dtype=np.float64)
+    inside = ref_rows[:, 0] >= 0
+    q = fc[sel][inside]
+    gotl = np.stack([Ul, Vl, Wl]).reshape(3, -1)[:, sel][:, inside]
+    expect = np.stack([2.0 + 0.5 * q[:, 0], -1.0 + 0.25 * q[:, 1] - 0.1 * q[:, 2], 0.3 * q[:, 2]])
+    assert np.abs(gotl - expect).max() <= 1e-9
+
+
+def test_linear_scattered_points_duplicates_and_errors():
+    """Non-rectilinear query points go through the point-query form; too few particles raise what Qhull
+    raises; the all-particles candidate path (tiny clouds, dense clouds per voxel) agrees with scipy."""
+    from scipy.spatial import QhullError
+    rng = np.random.default_rng(77)
+    pts = rng.uniform(0, 12, size=(3000, 3)).astype(np.float32).astype(np.float64)
+    vals = rng.normal(size=(3000, 3))
+    og, _ = rp.create_grid(((0, 12), (0, 12), (0, 12)), (9, 8, 7))
+    grid = tuple(a + 0.3 * rng.random(a.shape) for a in og)
+    res = gi.interpolate_field(_df(pts, vals), grid, method="linear", out_dtype=np.float64, return_knn=True)
+    ref = rp.interpolate_field(pts, vals, grid, method="linear")
+    _assert_vel(np.stack(res[:3]), np.stack(ref), vals)
+    ref_rows, _ = rp.delaunay_simplex_rows(pts, rp.flat_coords(grid))
+    assert np.array_equal(res[4], ref_rows)
+    with pytest.raises(QhullError):
+        gi.interpolate_field(_df(pts[:4], vals[:4]), og, method="linear")
+    # a dense cloud on a coarse grid (hundreds of particles per voxel) and a tiny cloud
+    for n, r in ((60000, (6, 5, 4)), (9, (7, 6, 5))):
+        p2 = rng.uniform(0, 12, size=(n, 3)).astype(np.float32).astype(np.float64)
+        v2 = rng.normal(size=(n, 3))
+        g2, _ = gi.create_grid(((0.5, 12.5), (0.5, 12.5), (0.5, 12.5)), r)
+        o2, _ = rp.create_grid(((0.5, 12.5), (0.5, 12.5), (0.5, 12.5)), r)
+        U, V, W = gi.interpolate_field(_df(p2, v2), g2, method="linear", out_dtype=np.float64)
+        _assert_vel(np.stack([U, V, W]), np.stack(rp.interpolate_field(p2, v2, o2, method="linear")), v2)

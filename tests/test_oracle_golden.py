@@ -173,3 +173,41 @@ def test_c_bruteforce_agrees_with_ckdtree_canonical(golden_dir):
     assert np.array_equal(ib, i) and np.array_equal(db, d)
     with pytest.raises(IndexError):
         knn_brute(pts[:5], q, 6)
+
+
+# ------------------------------------------------------------------ method='linear' (interpolator.py:197)
+def test_linear_port_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "case_i_linear.npz"))
+    for tag in ("a", "b"):
+        grid, _ = rp.create_grid(tuple(map(tuple, g[tag + "_bounds"])), tuple(int(r) for r in g[tag + "_res"]))
+        U, V, W = rp.interpolate_field(g[tag + "_points"], g[tag + "_values"], grid, method="linear")
+        assert np.array_equal(np.stack([U, V, W]), g[tag + "_uvw"])
+        rows, b = rp.delaunay_simplex_rows(g[tag + "_points"], rp.flat_coords(grid))
+        assert np.array_equal(rows, g[tag + "_simplex"])
+        inside = rows[:, 0] >= 0
+        vals = g[tag + "_values"]
+        rec = np.einsum("nk,nkc->nc", b[inside], vals[rows[inside]])
+        assert np.abs(rec - g[tag + "_uvw"].reshape(3, -1).T[inside]).max() <= 1e-12
+
+
+def test_linear_programme_restatement_matches_reference(golden_dir):
+    """oracle/delaunay_lp.py (no SciPy, no spatial index) finds the tetrahedra the reference evaluated in,
+    inside and outside the hull, and reproduces the reference on lattice (co-spherical) wall particles."""
+    from oracle.delaunay_lp import linear_interpolate
+    g = np.load(os.path.join(golden_dir, "case_i_linear.npz"))
+    rng = np.random.default_rng(0)
+    for tag in ("a", "b"):
+        grid, _ = rp.create_grid(tuple(map(tuple, g[tag + "_bounds"])), tuple(int(r) for r in g[tag + "_res"]))
+        fc = rp.flat_coords(grid)
+        sel = rng.choice(len(fc), 250, replace=False)
+        out, simp = linear_interpolate(g[tag + "_points"], g[tag + "_values"], fc[sel])
+        assert np.array_equal(simp, g[tag + "_simplex"][sel])
+        assert np.abs(out - g[tag + "_uvw"].reshape(3, -1).T[sel]).max() <= 1e-12
+    cb = np.load(os.path.join(golden_dir, "case_b_boundary.npz"))
+    grid, _ = rp.create_grid(((0, 12), (0, 12), (0, 12)), 12)
+    fc = rp.flat_coords(grid)
+    sel = rng.choice(len(fc), 250, replace=False)
+    ctr = cb["points"].mean(0)
+    q = fc[sel] + 2.0 ** -36 * (ctr - fc[sel])  # the kernel's nudge off the lattice planes
+    out, _ = linear_interpolate(cb["points"], cb["values"], q)
+    assert np.abs(out - g["c_uvw"].reshape(3, -1).T[sel]).max() <= 1e-8
