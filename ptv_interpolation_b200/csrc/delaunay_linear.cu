@@ -222,10 +222,33 @@ __device__ __forceinline__ bool find_violator(const KnnParams& p, const CandSet&
         });
   }
   if (cs.with_hull) {
-    for (int j = lane; j < p.hull_n; j += 32) {
-      const int4* src = reinterpret_cast<const int4*>(p.hull_rec + j);
-      const int4 a = __ldg(src), c = __ldg(src + 1);
-      consider(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(c.y, c.x), c.z);
+    // the list comes in chunks of 32 records with a bounding box each: the violation is a separable concave
+    // quadratic, so its maximum over a box is exact per axis -- a chunk that cannot hold a violator is skipped
+    const int nchunks = p.hull_n >> 5;
+    const double cut = 0.9 * best;
+    for (int base = 0; base < nchunks; base += 32) {
+      const int ch = base + lane;
+      bool flag = false;
+      if (ch < nchunks) {
+        const double* bb = p.hull_box + (size_t)ch * 6;
+        double ub = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double ta = a == 0 ? tx : (a == 1 ? ty : tz);
+          const double ca = a == 0 ? geo.cx : (a == 1 ? geo.cy : geo.cz);
+          const double ds = fmin(fmax(ca, bb[a] - ta), bb[3 + a] - ta);
+          ub += 2.0 * ca * ds - ds * ds;
+        }
+        flag = ub > cut;
+      }
+      unsigned todo = __ballot_sync(kFull, flag);
+      while (todo != 0) {
+        const int c = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int4* src = reinterpret_cast<const int4*>(p.hull_rec + ((size_t)(base + c) << 5) + lane);
+        const int4 a = __ldg(src), c4 = __ldg(src + 1);
+        consider(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(c4.y, c4.x), c4.z);
+      }
     }
   }
   double rb = best;
@@ -246,6 +269,41 @@ __device__ __forceinline__ bool find_violator(const KnnParams& p, const CandSet&
   return true;
 }
 
+// One dual-simplex pivot: particle (px,py,pz,pid) enters, the ratio test picks the vertex that leaves.
+__device__ __forceinline__ bool pivot(Tet& t, const Geo& geo, double qx, double qy, double qz, double px, double py,
+                                      double pz, int pid) {
+  double lam[4], mu[4];
+  bary(t, geo, qx, qy, qz, lam);
+  bary(t, geo, px, py, pz, mu);
+  int out = -1;
+  double bestr = INFINITY;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (mu[i] > 1e-14) {
+      const double r = fmax(lam[i], 0.0) / mu[i];
+      if (r < bestr) { bestr = r; out = i; }
+    }
+  }
+  if (out < 0) return false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i == out) { t.x[i] = px; t.y[i] = py; t.z[i] = pz; t.id[i] = pid; }
+  }
+  if (t.id[0] < 0) {  // keep a real vertex as the reference point: small magnitudes in the violation
+#pragma unroll
+    for (int i = 3; i >= 1; --i) {
+      if (t.id[i] >= 0 && t.id[0] < 0) {
+        double s;
+        s = t.x[0]; t.x[0] = t.x[i]; t.x[i] = s;
+        s = t.y[0]; t.y[0] = t.y[i]; t.y[i] = s;
+        s = t.z[0]; t.z[0] = t.z[i]; t.z[i] = s;
+        const int k = t.id[0]; t.id[0] = t.id[i]; t.id[i] = k;
+      }
+    }
+  }
+  return true;
+}
+
 // Dual-simplex pivots until no candidate lies inside the circumsphere.  (qx,qy,qz) is the nudged query.
 // Returns 0 when converged, 1 on the pivot limit / a degenerate step.
 __device__ __forceinline__ int lp_run(const KnnParams& p, const CandSet& cs, const WarpCache& wc, Tet& t, double qx,
@@ -256,38 +314,38 @@ __device__ __forceinline__ int lp_run(const KnnParams& p, const CandSet& cs, con
     double px, py, pz;
     int pid;
     if (!find_violator(p, cs, wc, t, geo, px, py, pz, pid)) return 0;
-    double lam[4], mu[4];
-    bary(t, geo, qx, qy, qz, lam);
-    bary(t, geo, px, py, pz, mu);
-    int out = -1;
-    double bestr = INFINITY;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (mu[i] > 1e-14) {
-        const double r = fmax(lam[i], 0.0) / mu[i];
-        if (r < bestr) { bestr = r; out = i; }
-      }
-    }
-    if (out < 0) return 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i == out) { t.x[i] = px; t.y[i] = py; t.z[i] = pz; t.id[i] = pid; }
-    }
-    if (t.id[0] < 0) {  // keep a real vertex as the reference point: small magnitudes in the violation
-#pragma unroll
-      for (int i = 3; i >= 1; --i) {
-        if (t.id[i] >= 0 && t.id[0] < 0) {
-          double s;
-          s = t.x[0]; t.x[0] = t.x[i]; t.x[i] = s;
-          s = t.y[0]; t.y[0] = t.y[i]; t.y[i] = s;
-          s = t.z[0]; t.z[0] = t.z[i]; t.z[i] = s;
-          const int k = t.id[0]; t.id[0] = t.id[i]; t.id[i] = k;
-        }
-      }
-    }
+    if (!pivot(t, geo, qx, qy, qz, px, py, pz, pid)) return 1;
     ++pivots;
   }
   return 1;
+}
+
+// The same programme over just the four vertices of `seed` (the neighbouring voxel's tetrahedron), every
+// lane for itself: takes the tetrahedron from the huge virtual one down to the local scale without a
+// candidate scan.  Any outcome is a valid (dual-feasible) start for lp_run.
+__device__ __forceinline__ void lp_seed(const Tet& seed, Tet& t, double qx, double qy, double qz) {
+  for (int it = 0; it < 8; ++it) {
+    Geo geo;
+    tet_geo(t, geo);
+    const double c2x = 2.0 * geo.cx, c2y = 2.0 * geo.cy, c2z = 2.0 * geo.cz;
+    double best = 1e-12 * fmax(geo.cc, 1e-300);
+    int bi = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double dx = seed.x[i] - t.x[0], dy = seed.y[i] - t.y[0], dz = seed.z[i] - t.z[0];
+      const double viol = (c2x * dx + c2y * dy + c2z * dz) - (dx * dx + dy * dy + dz * dz);
+      const int id = seed.id[i];
+      if (viol > best && id != t.id[0] && id != t.id[1] && id != t.id[2] && id != t.id[3]) { best = viol; bi = i; }
+    }
+    if (bi < 0) return;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    int pid = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i == bi) { px = seed.x[i]; py = seed.y[i]; pz = seed.z[i]; pid = seed.id[i]; }
+    }
+    if (!pivot(t, geo, qx, qy, qz, px, py, pz, pid)) return;
+  }
 }
 
 struct VoxelOut {
@@ -455,7 +513,7 @@ __global__ void __launch_bounds__(128) delaunay_linear_kernel(const KnnParams p)
       unsigned todo = act;
       if (cs.n >= 0) {
         Tet tet;
-        bool have = false;
+        bool have = false, have_seed = false;
         int pivots = 0, reused = 0, solved = 0;
         for (int i = 0; i < 32; ++i) {
           if (!((act >> i) & 1u)) continue;
@@ -471,7 +529,9 @@ __global__ void __launch_bounds__(128) delaunay_linear_kernel(const KnnParams p)
             reused += ok ? 1 : 0;
           }
           if (!ok) {
+            const Tet seed = tet;
             init_virtual(tet, x, y, z, Mv);
+            if (have_seed) lp_seed(seed, tet, xp, yp, zp);
             if (lp_run(p, cs, wc, tet, xp, yp, zp, pivots) == 0 && all_real(tet)) {
               Geo geo;
               tet_geo(tet, geo);
@@ -480,6 +540,7 @@ __global__ void __launch_bounds__(128) delaunay_linear_kernel(const KnnParams p)
             }
           }
           have = ok;
+          have_seed = all_real(tet);  // real vertices from this warp's cache: a good start for the next voxel
           if (ok) {
             VoxelOut o;
             emit(p, tet, x, y, z, o);
@@ -596,19 +657,74 @@ __global__ void hull_dominance_kernel(int cny, int cnz, const int* __restrict__ 
   }
 }
 
-__global__ void hull_compact_kernel(const ParticleRec* __restrict__ rec, const int32_t* __restrict__ cid, int64_t n,
-                                    int cnx, int nrows, const int* __restrict__ tab, ParticleRec* __restrict__ out,
-                                    int* __restrict__ count) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const ParticleRec r = rec[i];
-  const int c = cid[r.idx];
-  const int cx = c % cnx, row = c / cnx;
-  bool dominated = true;
+// One warp walks a run of kHullRun consecutive (cell-sorted) records and keeps the undominated ones in
+// order; the run's output is padded to a multiple of 32 with copies of its last record, so every chunk of
+// 32 output records comes from one run and is spatially compact.
+constexpr int kHullRun = 4096;
+__global__ void __launch_bounds__(128) hull_compact_kernel(const ParticleRec* __restrict__ rec,
+                                                           const int32_t* __restrict__ cid, int64_t n, int cnx,
+                                                           int nrows, const int* __restrict__ tab,
+                                                           ParticleRec* __restrict__ out, int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t run = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int64_t i0 = run * kHullRun;
+  if (i0 >= n) return;
+  const int64_t i1 = i0 + kHullRun < n ? i0 + kHullRun : n;
+  auto keep = [&](const ParticleRec& r) {
+    const int c = cid[r.idx];
+    const int cx = c % cnx, row = c / cnx;
+    bool dominated = true;
 #pragma unroll
-  for (int combo = 0; combo < 4; ++combo)
-    dominated = dominated && tab[combo * nrows + row] > cx && tab[(4 + combo) * nrows + row] < cx;
-  if (!dominated) out[atomicAdd(count, 1)] = r;
+    for (int combo = 0; combo < 4; ++combo)
+      dominated = dominated && tab[combo * nrows + row] > cx && tab[(4 + combo) * nrows + row] < cx;
+    return !dominated;
+  };
+  int total = 0;
+  for (int64_t i = i0 + lane; i < i0 + kHullRun; i += 32) {
+    const bool k = i < i1 && keep(rec[i]);
+    total += __popc(__ballot_sync(kFull, k));
+  }
+  if (total == 0) return;
+  const int padded = (total + 31) & ~31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(count, padded);
+  base = __shfl_sync(kFull, base, 0);
+  int pos = 0;
+  ParticleRec last = rec[i0];
+  for (int64_t i = i0 + lane; i < i0 + kHullRun; i += 32) {
+    ParticleRec r = last;
+    bool k = false;
+    if (i < i1) { r = rec[i]; k = keep(r); }
+    const unsigned b = __ballot_sync(kFull, k);
+    if (k) out[base + pos + __popc(b & ((1u << lane) - 1u))] = r;
+    pos += __popc(b);
+    if (b != 0) {  // remember the run's latest kept record (all lanes)
+      const int src = 31 - __clz(b);
+      int4 a = *reinterpret_cast<const int4*>(&r), c = *(reinterpret_cast<const int4*>(&r) + 1);
+      a.x = __shfl_sync(kFull, a.x, src); a.y = __shfl_sync(kFull, a.y, src);
+      a.z = __shfl_sync(kFull, a.z, src); a.w = __shfl_sync(kFull, a.w, src);
+      c.x = __shfl_sync(kFull, c.x, src); c.y = __shfl_sync(kFull, c.y, src);
+      c.z = __shfl_sync(kFull, c.z, src); c.w = __shfl_sync(kFull, c.w, src);
+      *reinterpret_cast<int4*>(&last) = a;
+      *(reinterpret_cast<int4*>(&last) + 1) = c;
+    }
+  }
+  if (total + lane < padded) out[base + total + lane] = last;
+}
+
+// bounding box (lo xyz, hi xyz) of every chunk of 32 list records
+__global__ void hull_box_kernel(const ParticleRec* __restrict__ rec, int nchunks, double* __restrict__ box) {
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ch >= nchunks) return;
+  const ParticleRec r = rec[((size_t)ch << 5) + lane];
+  double v6[6] = {r.x, r.y, r.z, -r.x, -r.y, -r.z};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) v6[c] = fmin(v6[c], __shfl_xor_sync(kFull, v6[c], o));
+  }
+  if (lane < 6) box[(size_t)ch * 6 + lane] = lane < 3 ? v6[lane] : -v6[lane];
 }
 
 }  // namespace
@@ -624,12 +740,17 @@ int ensure_hull_list(ptv_hash* h, cudaStream_t stream) {
     PTV_CUDA(cudaMalloc(&h->hull_tab, (size_t)(12 * (int64_t)nrows + 4) * sizeof(int)));
     h->hull_cap_rows = nrows;
   }
-  if (h->hull_cap < h->n) {
+  const int64_t nruns = (h->n + kHullRun - 1) / kHullRun;
+  const int64_t need = h->n + 32 * nruns;  // every run may pad its output up to a multiple of 32
+  if (h->hull_cap < need) {
     cudaFree(h->hull_rec);
+    cudaFree(h->hull_box);
     h->hull_rec = nullptr;
+    h->hull_box = nullptr;
     h->hull_cap = 0;
-    PTV_CUDA(cudaMalloc(&h->hull_rec, (size_t)h->n * sizeof(ParticleRec)));
-    h->hull_cap = h->n;
+    PTV_CUDA(cudaMalloc(&h->hull_rec, (size_t)need * sizeof(ParticleRec)));
+    PTV_CUDA(cudaMalloc(&h->hull_box, (size_t)(need / 32 + 1) * 6 * sizeof(double)));
+    h->hull_cap = need;
   }
   int* rowmin = h->hull_tab;
   int* rowmax = rowmin + nrows;
@@ -639,14 +760,19 @@ int ensure_hull_list(ptv_hash* h, cudaStream_t stream) {
   PTV_CUDA(cudaMemsetAsync(count, 0, sizeof(int), stream));
   hull_row_extent_kernel<<<(nrows + 127) / 128, 128, 0, stream>>>(h->cell_start, cnx, nrows, rowmin, rowmax);
   hull_dominance_kernel<<<1, 512, 0, stream>>>(cny, cnz, rowmin, rowmax, tmp, tab);
-  hull_compact_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, stream>>>(h->rec, h->cid, h->n, cnx, nrows, tab,
-                                                                         h->hull_rec, count);
+  hull_compact_kernel<<<(unsigned)((nruns + 3) / 4), 128, 0, stream>>>(h->rec, h->cid, h->n, cnx, nrows, tab,
+                                                                      h->hull_rec, count);
   count_launches(3);
   PTV_CUDA(cudaGetLastError());
   int host = 0;
   PTV_CUDA(cudaMemcpyAsync(&host, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
   PTV_CUDA(cudaStreamSynchronize(stream));
   h->hull_n = host;
+  if (host > 0) {
+    hull_box_kernel<<<(host / 32 + 3) / 4, 128, 0, stream>>>(h->hull_rec, host / 32, h->hull_box);
+    count_launches(1);
+    PTV_CUDA(cudaGetLastError());
+  }
   h->hull_valid = true;
   return PTV_OK;
 }

@@ -45,7 +45,8 @@ struct KnnParams {
   double* kth_dist;
   double mad_threshold;
   // method='linear' (delaunay_linear.cu): particles that may be convex-hull vertices (NULL = scan all)
-  const ParticleRec* hull_rec;
+  const ParticleRec* hull_rec;  // chunks of 32 records
+  const double* hull_box;       // [hull_n / 32][6] bounding box of each chunk
   int hull_n;
 };
 

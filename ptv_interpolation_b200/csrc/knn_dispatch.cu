@@ -66,6 +66,7 @@ static int run_linear(ptv_hash* h, KnnParams& p, bool f32, cudaStream_t stream) 
     rc = ensure_hull_list(h, stream);
     if (rc != PTV_OK) return rc;
     p.hull_rec = h->hull_rec;
+    p.hull_box = h->hull_box;
     p.hull_n = h->hull_n;
   }
   h->last_used_stream = false;
@@ -126,7 +127,7 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.qrec = nullptr; p.nq = 0; p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
   p.tiles_x = p.tiles_y = p.tiles_z = 0;
-  p.hull_rec = nullptr; p.hull_n = 0;
+  p.hull_rec = nullptr; p.hull_box = nullptr; p.hull_n = 0;
   if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
   if (method == PTV_METHOD_LINEAR) return run_linear(h, p, out_dtype == PTV_F32, stream);
 
@@ -195,7 +196,7 @@ static void init_point_params(KnnParams& p, const ptv_hash* h, const ptv_hash* q
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.qrec = q->rec; p.nq = q->n;
   p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
-  p.hull_rec = nullptr; p.hull_n = 0;
+  p.hull_rec = nullptr; p.hull_box = nullptr; p.hull_n = 0;
 }
 
 static int pick_heap_tile(int k, int method) {

@@ -78,6 +78,7 @@ struct ptv_hash {
   unsigned long long* fail_count = nullptr;  // [0] low 32 bits: fail count; [1]: streamed tiles (stats)
   // method='linear': hull-candidate records and the dominance tables they come from (built on demand)
   ptv::ParticleRec* hull_rec = nullptr;
+  double* hull_box = nullptr;
   int64_t hull_cap = 0;
   int* hull_tab = nullptr;
   int hull_cap_rows = 0;
