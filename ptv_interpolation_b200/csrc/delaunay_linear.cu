@@ -378,59 +378,89 @@ __device__ __forceinline__ void stat_add(const KnnParams& p, int slot, unsigned 
   if (p.stats != nullptr && (threadIdx.x & 31) == 0) atomicAdd(p.stats + slot, v);
 }
 
-// One voxel on its own: growing region around q, then (if a hull list exists) region U hull list.  The
-// programme only ever gains constraints, so the tetrahedron (virtual vertices included) carries over
-// from level to level.  Returns true with a verified tetrahedron in t, false if q is outside the hull
-// (or unresolved).
-__device__ bool solve_general(const KnnParams& p, WarpCache& wc, double qx, double qy, double qz, double qpx,
-                              double qpy, double qpz, double r_first, double M, Tet& t) {
+// Finish a voxel whose tetrahedron t has converged on the candidate set cs (cached in wc).  Every pivot
+// raises the objective of the programme and keeps q inside, whatever set the entering particle was drawn
+// from, so the search is free to look where it pays:
+//   * virtual vertices left: q is outside the hull of its neighbourhood -> add the hull-candidate list;
+//     still virtual -> outside the hull;
+//   * verification by the sphere itself: scan the cells the circumsphere touches (from shared memory if
+//     they fit, else straight from global memory, one pivot per scan so that the next scan follows the
+//     smaller sphere); a violator shrinks the sphere, no violator proves it empty.
+// r_cov: the set of cs covers B(q, r_cov) -- a sphere inside it needs no scan.  `clobbered` is set when the
+// warp cache was overwritten.  Returns kVerified, kOutside, kFailed or kVirtual (no hull list: the caller
+// must widen the region).
+enum { kVerified = 0, kOutside = 1, kFailed = 2, kVirtual = 3 };
+__device__ int finish_voxel(const KnnParams& p, WarpCache& wc, CandSet& cs, double qx, double qy, double qz,
+                            double qpx, double qpy, double qpz, double r_cov, Tet& t, int& pivots,
+                            bool& clobbered) {
+  const HashGrid& g = p.g;
+  const double margin = 1e-6 * g.cell;
+  if (!all_real(t)) {
+    if (p.hull_rec == nullptr) return kVirtual;
+    cs.with_hull = true;
+    const int rc = lp_run(p, cs, wc, t, qpx, qpy, qpz, pivots);
+    cs.with_hull = false;
+    if (rc != 0) return kFailed;
+    if (!all_real(t)) return kOutside;  // the programme over a superset of the hull vertices is unbounded
+  }
+  bool first = true;
+  for (;;) {
+    Geo geo;
+    tet_geo(t, geo);
+    const double ccx = t.x[0] + geo.cx, ccy = t.y[0] + geo.cy, ccz = t.z[0] + geo.cz, rad = sqrt(geo.cc);
+    if (first) {
+      const double ddx = ccx - qx, ddy = ccy - qy, ddz = ccz - qz;
+      if (sqrt(ddx * ddx + ddy * ddy + ddz * ddz) + rad <= r_cov - margin) return kVerified;
+      first = false;
+    }
+    CandSet sp;
+    sp.tg.lo[0] = sp.tg.hi[0] = ccx;
+    sp.tg.lo[1] = sp.tg.hi[1] = ccy;
+    sp.tg.lo[2] = sp.tg.hi[2] = ccz;
+    set_rmax(g, sp.tg);
+    sp.rg = make_region(g, sp.tg, fmin(rad * (1.0 + 1e-9) + 2.0 * margin, sp.tg.rmax));
+    sp.with_hull = false;
+    sp.n = warp_gather(g, sp.tg, sp.rg, wc);
+    clobbered = true;
+    const int before = pivots;
+    if (sp.n >= 0) {
+      if (lp_run(p, sp, wc, t, qpx, qpy, qpz, pivots) != 0) return kFailed;
+    } else {
+      stat_add(p, 3, 1);
+      double px, py, pz;
+      int pid;
+      if (find_violator(p, sp, wc, t, geo, px, py, pz, pid)) {
+        if (!pivot(t, geo, qpx, qpy, qpz, px, py, pz, pid) || ++pivots > 4 * kMaxPivots) return kFailed;
+      }
+    }
+    if (pivots == before) return kVerified;  // nothing inside the sphere
+  }
+}
+
+// One voxel from scratch (the warp's shared candidate set did not fit the cache, or there is no hull list
+// and the neighbourhood must grow until it covers the cloud).
+__device__ int solve_general(const KnnParams& p, WarpCache& wc, double qx, double qy, double qz, double qpx,
+                             double qpy, double qpz, double r_first, double M, Tet& t, int& pivots) {
   const HashGrid& g = p.g;
   CandSet cs;
   cs.tg.lo[0] = cs.tg.hi[0] = qx;
   cs.tg.lo[1] = cs.tg.hi[1] = qy;
   cs.tg.lo[2] = cs.tg.hi[2] = qz;
   set_rmax(g, cs.tg);
-  const double rmax = cs.tg.rmax;
-  const double margin = 1e-6 * g.cell;
-  const bool has_hull = p.hull_rec != nullptr;
-  double R = r_first;
-  bool final_level = false;
-  int pivots = 0;
-  stat_add(p, 2, 1);
+  double R = fmin(r_first, cs.tg.rmax);
   init_virtual(t, qx, qy, qz, M);
   for (;;) {
-    if (R >= rmax) R = rmax;
-    const bool covers_all = R >= rmax;
-    cs.with_hull = final_level && !covers_all;
+    const bool covers_all = R >= cs.tg.rmax;
     cs.rg = make_region(g, cs.tg, R);
+    cs.with_hull = false;
     cs.n = warp_gather(g, cs.tg, cs.rg, wc);
     if (cs.n < 0) stat_add(p, 3, 1);
-    const int rc = lp_run(p, cs, wc, t, qpx, qpy, qpz, pivots);
-    if (rc != 0) {
-      stat_add(p, 5, 1);
-      stat_add(p, 6, pivots);
-      return false;
-    }
-    if (all_real(t)) {
-      Geo geo;
-      tet_geo(t, geo);
-      const double ddx = t.x[0] + geo.cx - qx, ddy = t.y[0] + geo.cy - qy, ddz = t.z[0] + geo.cz - qz;
-      const double need = sqrt(ddx * ddx + ddy * ddy + ddz * ddz) + sqrt(geo.cc);
-      if (covers_all || need <= R - margin) {
-        stat_add(p, 6, pivots);
-        return true;
-      }
-      // grow towards the sphere, but not in one leap: nearer particles usually shrink it first
-      R = fmax(1.6 * R, fmin(need * (1.0 + 1e-9) + 2.0 * margin, 2.5 * R));
-    } else {
-      if (covers_all || cs.with_hull) {  // the programme over a superset of the hull vertices is unbounded
-        stat_add(p, 4, 1);
-        stat_add(p, 6, pivots);
-        return false;
-      }
-      if (has_hull) final_level = true;  // q is outside the hull of its neighbourhood: ask the hull list
-      else R *= 1.6;
-    }
+    if (lp_run(p, cs, wc, t, qpx, qpy, qpz, pivots) != 0) return kFailed;
+    bool clobbered = false;
+    const int rc = finish_voxel(p, wc, cs, qx, qy, qz, qpx, qpy, qpz, R, t, pivots, clobbered);
+    if (rc != kVirtual) return rc;
+    if (covers_all) return kOutside;
+    R = fmin(1.6 * R, cs.tg.rmax);
   }
 }
 
@@ -511,47 +541,64 @@ __global__ void __launch_bounds__(128) delaunay_linear_kernel(const KnnParams p)
       cs.with_hull = false;
       cs.n = warp_gather(g, cs.tg, cs.rg, wc);
       unsigned todo = act;
+      int pivots = 0, reused = 0, solved = 0, general = 0, outside = 0, failed = 0;
       if (cs.n >= 0) {
         Tet tet;
         bool have = false, have_seed = false;
-        int pivots = 0, reused = 0, solved = 0;
         for (int i = 0; i < 32; ++i) {
           if (!((act >> i) & 1u)) continue;
           const double x = __shfl_sync(kFull, qx, i), y = __shfl_sync(kFull, qy, i), z = __shfl_sync(kFull, qz, i);
           const double xp = x + kEta * (ctr[0] - x), yp = y + kEta * (ctr[1] - y), zp = z + kEta * (ctr[2] - z);
-          bool ok = false;
+          int rc = kFailed;
           if (have) {  // still inside the previous voxel's (verified) tetrahedron?
             Geo geo;
             tet_geo(tet, geo);
             double b[4];
             bary(tet, geo, xp, yp, zp, b);
-            ok = b[0] >= 0.0 && b[1] >= 0.0 && b[2] >= 0.0 && b[3] >= 0.0;
-            reused += ok ? 1 : 0;
+            if (b[0] >= 0.0 && b[1] >= 0.0 && b[2] >= 0.0 && b[3] >= 0.0) {
+              rc = kVerified;
+              ++reused;
+            }
           }
-          if (!ok) {
+          if (rc != kVerified) {
             const Tet seed = tet;
             init_virtual(tet, x, y, z, Mv);
             if (have_seed) lp_seed(seed, tet, xp, yp, zp);
-            if (lp_run(p, cs, wc, tet, xp, yp, zp, pivots) == 0 && all_real(tet)) {
-              Geo geo;
-              tet_geo(tet, geo);
-              const double d = box_dist(cs.tg, tet.x[0] + geo.cx, tet.y[0] + geo.cy, tet.z[0] + geo.cz);
-              ok = d + sqrt(geo.cc) <= R - margin;  // the sphere lies inside the gathered region: verified
+            if (lp_run(p, cs, wc, tet, xp, yp, zp, pivots) == 0) {
+              have_seed = all_real(tet);  // real vertices from this warp's cache: a good start for the next voxel
+              bool inside = false;
+              if (have_seed) {
+                Geo geo;
+                tet_geo(tet, geo);
+                const double d = box_dist(cs.tg, tet.x[0] + geo.cx, tet.y[0] + geo.cy, tet.z[0] + geo.cz);
+                inside = d + sqrt(geo.cc) <= R - margin;  // the sphere lies inside the gathered region: verified
+              }
+              if (inside) {
+                rc = kVerified;
+                ++solved;
+              } else {
+                bool clobbered = false;
+                ++general;
+                rc = finish_voxel(p, wc, cs, x, y, z, xp, yp, zp, 0.0, tet, pivots, clobbered);
+                if (clobbered) cs.n = warp_gather(g, cs.tg, cs.rg, wc);
+              }
+            } else {
+              have_seed = false;
             }
           }
-          have = ok;
-          have_seed = all_real(tet);  // real vertices from this warp's cache: a good start for the next voxel
-          if (ok) {
+          have = rc == kVerified;
+          if (rc == kVirtual) continue;  // no hull list: solved from scratch below
+          todo &= ~(1u << i);
+          if (rc == kVerified) {
             VoxelOut o;
             emit(p, tet, x, y, z, o);
             if (lane == i) mine = o;
-            todo &= ~(1u << i);
-            ++solved;
+          } else if (rc == kOutside) {
+            ++outside;
+          } else {
+            ++failed;
           }
         }
-        stat_add(p, 0, solved);
-        stat_add(p, 1, reused);
-        stat_add(p, 6, pivots);
       } else {
         stat_add(p, 3, 1);
       }
@@ -561,12 +608,24 @@ __global__ void __launch_bounds__(128) delaunay_linear_kernel(const KnnParams p)
         const double x = __shfl_sync(kFull, qx, i), y = __shfl_sync(kFull, qy, i), z = __shfl_sync(kFull, qz, i);
         const double xp = x + kEta * (ctr[0] - x), yp = y + kEta * (ctr[1] - y), zp = z + kEta * (ctr[2] - z);
         Tet tet;
-        if (solve_general(p, wc, x, y, z, xp, yp, zp, r_first, Mv, tet)) {
+        ++general;
+        const int rc = solve_general(p, wc, x, y, z, xp, yp, zp, r_first, Mv, tet, pivots);
+        if (rc == kVerified) {
           VoxelOut o;
           emit(p, tet, x, y, z, o);
           if (lane == i) mine = o;
+        } else if (rc == kOutside) {
+          ++outside;
+        } else {
+          ++failed;
         }
       }
+      stat_add(p, 0, solved);
+      stat_add(p, 1, reused);
+      stat_add(p, 2, general);
+      stat_add(p, 4, outside);
+      stat_add(p, 5, failed);
+      stat_add(p, 6, pivots);
     }
   }
 
