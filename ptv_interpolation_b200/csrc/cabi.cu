@@ -57,6 +57,7 @@ extern "C" int ptv_set_tuning(const char* key, double value) {
   else if (!strcmp(key, "stream_tile")) t.stream_tile = (int)value;
   else if (!strcmp(key, "stats")) t.stats = (int)value;
   else if (!strcmp(key, "hull")) t.hull = (int)value;
+  else if (!strcmp(key, "linear_occ")) t.linear_occ = (int)value;
   else if (!strcmp(key, "rscale")) { if (!(value >= 1.0 && value <= 4.0)) { set_error("rscale must be in [1, 4]"); return PTV_ERR_INVALID; } t.rscale = value; }
   else { set_error(std::string("ptv_set_tuning: unknown key ") + key); return PTV_ERR_INVALID; }
   return PTV_OK;
@@ -72,6 +73,7 @@ extern "C" double ptv_get_tuning(const char* key) {
   if (!strcmp(key, "stream_tile")) return t.stream_tile;
   if (!strcmp(key, "stats")) return t.stats;
   if (!strcmp(key, "hull")) return t.hull;
+  if (!strcmp(key, "linear_occ")) return t.linear_occ;
   if (!strcmp(key, "rscale")) return t.rscale;
   return nan("");
 }

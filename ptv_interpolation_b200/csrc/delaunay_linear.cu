@@ -35,7 +35,7 @@
 namespace ptv {
 namespace {
 
-constexpr int kCap = 512;         // cached candidates per warp (28 B each)
+constexpr int kCap = 448;         // cached candidates per warp (28 B each): 4 CTAs of 4 warps per SM
 constexpr int kMaxPivots = 600;
 constexpr double kEta = 1.0 / 68719476736.0;  // 2^-36
 constexpr unsigned kFull = 0xffffffffu;
@@ -204,11 +204,9 @@ __device__ __forceinline__ bool find_violator(const KnnParams& p, const CandSet&
   auto consider = [&](double x, double y, double z, int id) {
     const double dx = x - tx, dy = y - ty, dz = z - tz;
     const double viol = (c2x * dx + c2y * dy + c2z * dz) - (dx * dx + dy * dy + dz * dz);
-    if (viol > best || (viol == best && id < bid)) {
-      if (id != t.id[0] && id != t.id[1] && id != t.id[2] && id != t.id[3]) {
-        best = viol; bid = id; bx = x; by = y; bz = z;
-      }
-    }
+    // (the tetrahedron's own vertices need no test: they lie ON the sphere, violation 0 up to rounding of
+    // ~1e-15 r^2, far below the 1e-12 r^2 threshold `best` starts from)
+    if (viol > best) { best = viol; bid = id; bx = x; by = y; bz = z; }
   };
   if (cs.n >= 0) {
     for (int j = lane; j < cs.n; j += 32) consider(wc.x[j], wc.y[j], wc.z[j], wc.idx[j]);
@@ -275,14 +273,13 @@ __device__ __forceinline__ bool pivot(Tet& t, const Geo& geo, double qx, double 
   double lam[4], mu[4];
   bary(t, geo, qx, qy, qz, lam);
   bary(t, geo, px, py, pz, mu);
+  // ratio test: the smallest lam_i / mu_i over mu_i > 0, compared by cross-multiplication (no divisions)
   int out = -1;
-  double bestr = INFINITY;
+  double bl = 0.0, bm = 1.0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (mu[i] > 1e-14) {
-      const double r = fmax(lam[i], 0.0) / mu[i];
-      if (r < bestr) { bestr = r; out = i; }
-    }
+    const double li = fmax(lam[i], 0.0);
+    if (mu[i] > 1e-14 && (out < 0 || li * bm < bl * mu[i])) { bl = li; bm = mu[i]; out = i; }
   }
   if (out < 0) return false;
 #pragma unroll
@@ -464,8 +461,8 @@ __device__ int solve_general(const KnnParams& p, WarpCache& wc, double qx, doubl
   }
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(128) delaunay_linear_kernel(const KnnParams p) {
+template <typename OutT, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) delaunay_linear_kernel(const KnnParams p) {
   constexpr int T = 128, TX = 8, TY = 4, TZ = 4, NW = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpCache* cache = reinterpret_cast<WarpCache*>(smem_raw);  // [NW]
@@ -849,13 +846,11 @@ int launch_delaunay_linear(KnnParams& p, bool f32, cudaStream_t stream) {
   const int64_t ntiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
   if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
   const size_t smem = 4 * sizeof(WarpCache);
-  if (f32) {
-    PTV_CUDA(cudaFuncSetAttribute(delaunay_linear_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    delaunay_linear_kernel<float><<<(unsigned)ntiles, T, smem, stream>>>(p);
-  } else {
-    PTV_CUDA(cudaFuncSetAttribute(delaunay_linear_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    delaunay_linear_kernel<double><<<(unsigned)ntiles, T, smem, stream>>>(p);
-  }
+  void (*kern)(const KnnParams);
+  if (tuning().linear_occ >= 4) kern = f32 ? delaunay_linear_kernel<float, 4> : delaunay_linear_kernel<double, 4>;
+  else kern = f32 ? delaunay_linear_kernel<float, 3> : delaunay_linear_kernel<double, 3>;
+  PTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)ntiles, T, smem, stream>>>(p);
   count_launches(1);
   PTV_CUDA(cudaGetLastError());
   return PTV_OK;

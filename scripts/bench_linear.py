@@ -13,7 +13,11 @@ dev = torch.device("cuda", 0)
 eng = PTVEngine(dev)
 out = {}
 set_tuning(stats=1)
-for name in (sys.argv[1:] or ["c1", "c2"]):
+names = [a for a in sys.argv[1:] if "=" not in a] or ["c1", "c2"]
+for a in sys.argv[1:]:
+    if "=" in a:
+        set_tuning(**{a.split("=")[0]: float(a.split("=")[1])})
+for name in names:
     cfg = synthetic.make_config(name, device=dev)
     n = cfg["n"]
     ax = torch.linspace(0, n - 1, n, dtype=torch.float64, device=dev)
