@@ -11,8 +11,9 @@ Differences a caller can observe (all documented in DESIGN.md):
     reference dtype), accepts an optional ``mask=`` to skip and zero solid voxels (what
     main.py:202-207 does afterwards), and writes 0 where the reference would produce NaN
     (main.py:195-199 replaces those by 0 anyway);
-  * ``method='linear'/'cubic'`` (Delaunay via griddata, interpolator.py:197) are not on the CUDA
-    path and raise NotImplementedError -- there is no CPU fallback.
+  * ``method='linear'`` (griddata / Qhull Delaunay, interpolator.py:197 -- the reference's default) runs
+    on the CUDA path without building a triangulation (csrc/delaunay_linear.cu); ``'cubic'`` raises the
+    ValueError griddata raises for 3-D data.
 """
 from __future__ import annotations
 

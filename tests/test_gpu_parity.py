@@ -355,6 +355,16 @@ def test_host_cabi_entry_point():
     rc = lib.ptv_interpolate_host(p(pts), p(vals), 5, p(ax[0]), 8, p(ax[1]), 7, p(ax[2]), 6, None,
                                   _cabi.METHOD_IDW, 12, 2.0, 0.0, _cabi.F32, p(out[0]), p(out[1]), p(out[2]))
     assert rc == _cabi.PTV_ERR_TOO_FEW and b"out of bounds" in lib.ptv_last_error()
+    # method='linear' (main.py's default) through the same host entry point, float64 output
+    out64 = np.zeros((3, 6, 7, 8), dtype=np.float64)
+    rc = lib.ptv_interpolate_host(p(pts), p(vals), 300, p(ax[0]), 8, p(ax[1]), 7, p(ax[2]), 6, None,
+                                  _cabi.METHOD_LINEAR, 0, 2.0, 0.0, _cabi.F64, p(out64[0]), p(out64[1]), p(out64[2]))
+    _cabi.check(rc)
+    Ul, Vl, Wl = rp.interpolate_field(pts, vals, (X, Y, Z), method="linear")
+    assert np.abs(out64 - np.stack([Ul, Vl, Wl])).max() <= 1e-11
+    rc = lib.ptv_interpolate_host(p(pts), p(vals), 4, p(ax[0]), 8, p(ax[1]), 7, p(ax[2]), 6, None,
+                                  _cabi.METHOD_LINEAR, 0, 2.0, 0.0, _cabi.F64, p(out64[0]), p(out64[1]), p(out64[2]))
+    assert rc == _cabi.PTV_ERR_QHULL and b"QH6214" in lib.ptv_last_error()
 
 
 # ------------------------------------------------------------------ local RBF (a8/a9)
@@ -771,6 +781,12 @@ def test_main_py_flow_steps_4_to_7():
     # the masked call gives the same field without the caller's zeroing
     Um, Vm, Wm = gi.interpolate_field(d_g, grid_g, method="idw", mask=mask_g, out_dtype=np.float64)
     assert np.abs(Um - U).max() <= 1e-11 and np.abs(Wm - W).max() <= 1e-11
+    # main.py's DEFAULT method (--method linear, main.py:33): same flow, Delaunay interpolation
+    Ul, Vl, Wl = gi.interpolate_field(d_g, grid_g, out_dtype=np.float64)
+    Ul[~mask_g] = 0; Vl[~mask_g] = 0; Wl[~mask_g] = 0
+    Ulr, Vlr, Wlr = rp.interpolate_field(d_r[["x", "y", "z"]].values, d_r[["u", "v", "w"]].values, grid_r, method="linear")
+    Ulr, Vlr, Wlr = rp.apply_mask_zero(Ulr, Vlr, Wlr, mask_r)
+    _assert_vel(np.stack([Ul, Vl, Wl]), np.stack([Ulr, Vlr, Wlr]), d_r[["u", "v", "w"]].values)
     dx, dy, dz = (float(a[1] - a[0]) for a in ax_g)
     uc, vc, wc = gp.clean_divergence(U, V, W, mask_g, dx, dy, dz, iterations=2)
     ucr, vcr, wcr = rp.clean_divergence_projection(Ur, Vr, Wr, mask_r, dx, dy, dz, iterations=2)
