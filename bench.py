@@ -366,13 +366,25 @@ def run_b200(args):
     roofline = {"kernel": "knn_stream_kernel (+ knn_interp_kernel on handed-over tiles)" if used_stream
                 else "knn_interp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full
-                # capture of this workload (profiles/r01_v3_knn_stream_c4_ncu_full.csv); null for other workloads
-                "traffic": 20.78e9 if (args.workload == "c4" and world == 1 and used_stream) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture of
+                # this workload (profiles/r01_v4_knn_stream_c4_ncu_metrics.csv); null for other workloads
+                "traffic": 21.52e9 if (args.workload == "c4" and world == 1 and used_stream) else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": knn_ms,
                 "note": "kNN selection is SM-issue bound, not HBM bound (DESIGN.md); the HBM-bound kernels are "
                         "listed under roofline_other"}
+    # What actually bounds that kernel: warp-instruction issue.  Instructions per launch come from the same
+    # committed ncu capture (smsp__inst_executed.sum); the time is this run's; peak = 148 SMs x 4 schedulers x
+    # one warp instruction per clock at the maximum SM clock.
+    roofline_issue = None
+    if args.workload == "c4" and world == 1 and used_stream:
+        issue_peak = 148 * 4 * 1.965e9
+        issue_ach = 2.288e11 / (knn_ms * 1e-3)
+        roofline_issue = {"kernel": "knn_stream_kernel", "bound": "sm_issue", "achieved": issue_ach / 1e9,
+                          "peak": issue_peak / 1e9, "unit": "G warp-inst/s", "frac": issue_ach / issue_peak,
+                          "warp_inst_per_launch": 2.288e11,
+                          "source": "profiles/r01_v4_knn_stream_c4_ncu_metrics.csv (smsp__inst_executed.sum; "
+                                    "smsp__issue_active 56.8 % in that capture)"}
     st_ms = float(np.mean(phase_ms["stencils"]))
     st_bytes = 17.0 * nzl * n * n  # fused divergence + flux + statistics: 12 B u,v,w + 1 B mask read, 4 B div written
     roofline_other = [{"kernel": "div_flux_kernel (1 launch + halo/reduce)", "bound": "hbm",
@@ -406,7 +418,8 @@ def run_b200(args):
                    "mask_skip": True, "all_voxels_per_sec": n ** 3 / (ms_per_step * 1e-3),
                    "phase_ms_rank0": {p: float(np.mean(v)) for p, v in phase_ms.items()},
                    "mean_abs_div": mean_abs_div},
-        "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "roofline": roofline, "roofline_issue": roofline_issue, "roofline_other": roofline_other,
+        "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
