@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) delaunay_linear_kernel(const 
     tile_geometry<T>(g, active, qx, qy, qz, red, tg);
     // radius expected to hold 64 particles = 2.5 mean spacings: Delaunay circumspheres of a voxel
     // (centre offset + radius) rarely reach further
-    const double r_est = estimate_radius<T>(g, tg, p.r0, 64, 16, warp_tot);
+    const double r_est = estimate_radius<T>(g, tg, p.r0, p.k, 16, warp_tot);
     const double r_first = r_est > 0.0 ? r_est : 2.0 * g.cell;
     // the virtual vertices: far enough that, over the extent of the cloud, a sphere through one of them is
     // a plane to 1e-4 of that extent
@@ -542,7 +542,10 @@ __global__ void __launch_bounds__(128, kMinBlocks) delaunay_linear_kernel(const 
       if (cs.n >= 0) {
         Tet tet;
         bool have = false, have_seed = false;
-        for (int i = 0; i < 32; ++i) {
+        for (int step = 0; step < 32; ++step) {
+          // boustrophedon through the 8x4 block: consecutive voxels are always neighbours, which is what the
+          // tetrahedron re-use and the seeds live on
+          const int i = (step & 8) ? (step ^ 7) : step;
           if (!((act >> i) & 1u)) continue;
           const double x = __shfl_sync(kFull, qx, i), y = __shfl_sync(kFull, qy, i), z = __shfl_sync(kFull, qz, i);
           const double xp = x + kEta * (ctr[0] - x), yp = y + kEta * (ctr[1] - y), zp = z + kEta * (ctr[2] - z);
@@ -623,6 +626,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) delaunay_linear_kernel(const 
       stat_add(p, 4, outside);
       stat_add(p, 5, failed);
       stat_add(p, 6, pivots);
+      if (failed > 0 && lane == 0) atomicAdd(p.err_flag, failed);  // surfaced by the host as an error
     }
   }
 

@@ -70,7 +70,20 @@ static int run_linear(ptv_hash* h, KnnParams& p, bool f32, cudaStream_t stream) 
     p.hull_n = h->hull_n;
   }
   h->last_used_stream = false;
-  return launch_delaunay_linear(p, f32, stream);
+  p.k = tuning().linear_k;  // first radius = the one expected to hold this many particles
+  PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
+  rc = launch_delaunay_linear(p, f32, stream);
+  if (rc != PTV_OK) return rc;
+  // a voxel whose programme hit the pivot limit was written as 0: never silently (Qhull reports its own
+  // precision failures as QhullError too)
+  PTV_CUDA(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PTV_CUDA(cudaStreamSynchronize(stream));
+  if (*h->err_host != 0) {
+    set_error("method='linear': " + std::to_string(*h->err_host) +
+              " voxel(s) could not be resolved (pivot limit reached: degenerate input?)");
+    return PTV_ERR_QHULL;
+  }
+  return PTV_OK;
 }
 
 static void tile_shape(int T, int& tx, int& ty, int& tz) {
