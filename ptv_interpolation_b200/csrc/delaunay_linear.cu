@@ -35,7 +35,7 @@
 namespace ptv {
 namespace {
 
-constexpr int kCap = 448;         // cached candidates per warp (28 B each): 4 CTAs of 4 warps per SM
+constexpr int kCap = 416;         // cached candidates per warp (32 B each): 4 CTAs of 4 warps per SM
 constexpr int kMaxPivots = 600;
 constexpr double kEta = 1.0 / 68719476736.0;  // 2^-36
 constexpr unsigned kFull = 0xffffffffu;
@@ -43,7 +43,18 @@ constexpr unsigned kFull = 0xffffffffu;
 struct WarpCache {
   double x[kCap], y[kCap], z[kCap];
   int idx[kCap];
+  float rd[kCap];  // 1 / |p - q|^2 for the voxel being solved (set_query)
 };
+
+// per-voxel part of the cache: reciprocal squared distances from the (nudged) query, used to scale violations
+__device__ __forceinline__ void set_query(WarpCache& wc, int n, double qx, double qy, double qz) {
+  __syncwarp();
+  for (int j = (threadIdx.x & 31); j < n; j += 32) {
+    const double ex = wc.x[j] - qx, ey = wc.y[j] - qy, ez = wc.z[j] - qz;
+    wc.rd[j] = __frcp_rn((float)(ex * ex + ey * ey + ez * ez));
+  }
+  __syncwarp();
+}
 
 struct Tet {
   double x[4], y[4], z[4];
@@ -189,41 +200,54 @@ __device__ __forceinline__ int warp_gather(const HashGrid& g, const TileGeom& tg
   return ok ? next : -1;
 }
 
-// The particle deepest inside the circumsphere of t (violation 2 c.d - d.d = r^2 - |p - centre|^2 with
-// d = p - v0), ties on the smaller particle row.  All lanes return the same answer.
+// The entering particle: among those strictly inside the circumsphere of t (violation 2 c.d - d.d =
+// r^2 - |p - centre|^2 > 1e-12 r^2, d = p - v0) the one with the largest violation per squared distance
+// from the query.  Any violator is a valid pivot; the deepest one is a poor choice while virtual vertices
+// make the "sphere" a half-space (it is the FARTHEST particle on that side), the scaled rule prefers
+// particles near q and reaches the local scale in fewer pivots.  Ties go to the smaller particle row; all
+// lanes return the same answer.
 __device__ __forceinline__ bool find_violator(const KnnParams& p, const CandSet& cs, const WarpCache& wc,
-                                              const Tet& t, const Geo& geo, double& px, double& py, double& pz,
-                                              int& pid) {
+                                              const Tet& t, const Geo& geo, double qx, double qy, double qz,
+                                              double& px, double& py, double& pz, int& pid) {
   const int lane = threadIdx.x & 31;
   const HashGrid& g = p.g;
-  double best = 1e-12 * fmax(geo.cc, 1e-300);
+  const double tolv = 1e-12 * fmax(geo.cc, 1e-300);
   int bid = INT_MAX;
   double bx = 0.0, by = 0.0, bz = 0.0;
   const double tx = t.x[0], ty = t.y[0], tz = t.z[0];
   const double c2x = 2.0 * geo.cx, c2y = 2.0 * geo.cy, c2z = 2.0 * geo.cz;
-  auto consider = [&](double x, double y, double z, int id) {
+  float best = 0.0f;
+  auto consider = [&](double x, double y, double z, int id, float rdist) {
     const double dx = x - tx, dy = y - ty, dz = z - tz;
     const double viol = (c2x * dx + c2y * dy + c2z * dz) - (dx * dx + dy * dy + dz * dz);
     // (the tetrahedron's own vertices need no test: they lie ON the sphere, violation 0 up to rounding of
-    // ~1e-15 r^2, far below the 1e-12 r^2 threshold `best` starts from)
-    if (viol > best) { best = viol; bid = id; bx = x; by = y; bz = z; }
+    // ~1e-15 r^2, far below the threshold)
+    if (viol > tolv) {
+      const float score = fmaxf((float)viol * rdist, 1e-37f);  // float32 is plenty for a preference
+      if (score > best) { best = score; bid = id; bx = x; by = y; bz = z; }
+    }
+  };
+  auto rdist_of = [&](double x, double y, double z) {
+    const double ex = x - qx, ey = y - qy, ez = z - qz;
+    return __frcp_rn((float)(ex * ex + ey * ey + ez * ez));
   };
   if (cs.n >= 0) {
-    for (int j = lane; j < cs.n; j += 32) consider(wc.x[j], wc.y[j], wc.z[j], wc.idx[j]);
+    for (int j = lane; j < cs.n; j += 32) consider(wc.x[j], wc.y[j], wc.z[j], wc.idx[j], wc.rd[j]);
   } else {
     for_each_region_record(
         g, cs.tg, cs.rg, [](int) { return true; },
         [&](int, int r) {
           const int4* src = reinterpret_cast<const int4*>(g.rec + r);
           const int4 a = __ldg(src), c = __ldg(src + 1);
-          consider(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(c.y, c.x), c.z);
+          const double x = __hiloint2double(a.y, a.x), y = __hiloint2double(a.w, a.z), z = __hiloint2double(c.y, c.x);
+          consider(x, y, z, c.z, rdist_of(x, y, z));
         });
   }
   if (cs.with_hull) {
     // the list comes in chunks of 32 records with a bounding box each: the violation is a separable concave
     // quadratic, so its maximum over a box is exact per axis -- a chunk that cannot hold a violator is skipped
     const int nchunks = p.hull_n >> 5;
-    const double cut = 0.9 * best;
+    const double cut = 0.9 * tolv;
     for (int base = 0; base < nchunks; base += 32) {
       const int ch = base + lane;
       bool flag = false;
@@ -245,15 +269,16 @@ __device__ __forceinline__ bool find_violator(const KnnParams& p, const CandSet&
         todo &= todo - 1;
         const int4* src = reinterpret_cast<const int4*>(p.hull_rec + ((size_t)(base + c) << 5) + lane);
         const int4 a = __ldg(src), c4 = __ldg(src + 1);
-        consider(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(c4.y, c4.x), c4.z);
+        const double x = __hiloint2double(a.y, a.x), y = __hiloint2double(a.w, a.z), z = __hiloint2double(c4.y, c4.x);
+        consider(x, y, z, c4.z, rdist_of(x, y, z));
       }
     }
   }
-  double rb = best;
+  float rb = best;
   int ri = bid;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(kFull, rb, o);
+    const float ob = __shfl_xor_sync(kFull, rb, o);
     const int oi = __shfl_xor_sync(kFull, ri, o);
     if (ob > rb || (ob == rb && oi < ri)) { rb = ob; ri = oi; }
   }
@@ -310,7 +335,7 @@ __device__ __forceinline__ int lp_run(const KnnParams& p, const CandSet& cs, con
     tet_geo(t, geo);
     double px, py, pz;
     int pid;
-    if (!find_violator(p, cs, wc, t, geo, px, py, pz, pid)) return 0;
+    if (!find_violator(p, cs, wc, t, geo, qx, qy, qz, px, py, pz, pid)) return 0;
     if (!pivot(t, geo, qx, qy, qz, px, py, pz, pid)) return 1;
     ++pivots;
   }
@@ -421,12 +446,13 @@ __device__ int finish_voxel(const KnnParams& p, WarpCache& wc, CandSet& cs, doub
     clobbered = true;
     const int before = pivots;
     if (sp.n >= 0) {
+      set_query(wc, sp.n, qpx, qpy, qpz);
       if (lp_run(p, sp, wc, t, qpx, qpy, qpz, pivots) != 0) return kFailed;
     } else {
       stat_add(p, 3, 1);
       double px, py, pz;
       int pid;
-      if (find_violator(p, sp, wc, t, geo, px, py, pz, pid)) {
+      if (find_violator(p, sp, wc, t, geo, qpx, qpy, qpz, px, py, pz, pid)) {
         if (!pivot(t, geo, qpx, qpy, qpz, px, py, pz, pid) || ++pivots > 4 * kMaxPivots) return kFailed;
       }
     }
@@ -452,6 +478,7 @@ __device__ int solve_general(const KnnParams& p, WarpCache& wc, double qx, doubl
     cs.with_hull = false;
     cs.n = warp_gather(g, cs.tg, cs.rg, wc);
     if (cs.n < 0) stat_add(p, 3, 1);
+    else set_query(wc, cs.n, qpx, qpy, qpz);
     if (lp_run(p, cs, wc, t, qpx, qpy, qpz, pivots) != 0) return kFailed;
     bool clobbered = false;
     const int rc = finish_voxel(p, wc, cs, qx, qy, qz, qpx, qpy, qpz, R, t, pivots, clobbered);
@@ -564,6 +591,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) delaunay_linear_kernel(const 
             const Tet seed = tet;
             init_virtual(tet, x, y, z, Mv);
             if (have_seed) lp_seed(seed, tet, xp, yp, zp);
+            set_query(wc, cs.n, xp, yp, zp);
             if (lp_run(p, cs, wc, tet, xp, yp, zp, pivots) == 0) {
               have_seed = all_real(tet);  // real vertices from this warp's cache: a good start for the next voxel
               bool inside = false;
@@ -721,16 +749,19 @@ __global__ void hull_dominance_kernel(int cny, int cnz, const int* __restrict__ 
 // order; the run's output is padded to a multiple of 32 with copies of its last record, so every chunk of
 // 32 output records comes from one run and is spatially compact.
 constexpr int kHullRun = 4096;
+// flags != nullptr: keep record i iff flags[i] (stage 2); else the cell-dominance test (stage 1)
 __global__ void __launch_bounds__(128) hull_compact_kernel(const ParticleRec* __restrict__ rec,
                                                            const int32_t* __restrict__ cid, int64_t n, int cnx,
                                                            int nrows, const int* __restrict__ tab,
+                                                           const uint8_t* __restrict__ flags,
                                                            ParticleRec* __restrict__ out, int* __restrict__ count) {
   const int lane = threadIdx.x & 31;
   const int64_t run = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int64_t i0 = run * kHullRun;
   if (i0 >= n) return;
   const int64_t i1 = i0 + kHullRun < n ? i0 + kHullRun : n;
-  auto keep = [&](const ParticleRec& r) {
+  auto keep = [&](const ParticleRec& r, int64_t i) {
+    if (flags != nullptr) return flags[i] != 0;
     const int c = cid[r.idx];
     const int cx = c % cnx, row = c / cnx;
     bool dominated = true;
@@ -741,7 +772,7 @@ __global__ void __launch_bounds__(128) hull_compact_kernel(const ParticleRec* __
   };
   int total = 0;
   for (int64_t i = i0 + lane; i < i0 + kHullRun; i += 32) {
-    const bool k = i < i1 && keep(rec[i]);
+    const bool k = i < i1 && keep(rec[i], i);
     total += __popc(__ballot_sync(kFull, k));
   }
   if (total == 0) return;
@@ -754,7 +785,7 @@ __global__ void __launch_bounds__(128) hull_compact_kernel(const ParticleRec* __
   for (int64_t i = i0 + lane; i < i0 + kHullRun; i += 32) {
     ParticleRec r = last;
     bool k = false;
-    if (i < i1) { r = rec[i]; k = keep(r); }
+    if (i < i1) { r = rec[i]; k = keep(r, i); }
     const unsigned b = __ballot_sync(kFull, k);
     if (k) out[base + pos + __popc(b & ((1u << lane) - 1u))] = r;
     pos += __popc(b);
@@ -770,6 +801,50 @@ __global__ void __launch_bounds__(128) hull_compact_kernel(const ParticleRec* __
     }
   }
   if (total + lane < padded) out[base + total + lane] = last;
+}
+
+// Stage 2, per particle of the stage-1 list: p is an extreme point of the cloud only if some CLOSED octant
+// around it holds no other particle (if every closed octant {s_i (x_i' - x_i) >= 0} held one, any direction
+// n would have n.(p' - p) >= 0 for the p' in the octant of sign(n): p is not strictly separable from the
+// rest, i.e. p lies in their hull).  Closed octants also retire the interior points of flat faces (wall
+// particles on a lattice plane).  The search walks cell rows outwards from p's cell and stops at the
+// first hit; an octant that costs more than kRefineBudget row visits keeps p (conservative).
+constexpr int kRefineBudget = 1 << 16;
+__global__ void __launch_bounds__(128) hull_refine_kernel(const ParticleRec* __restrict__ list, int n1,
+                                                          const ParticleRec* __restrict__ rec,
+                                                          const int32_t* __restrict__ cell_start,
+                                                          const int32_t* __restrict__ cid, int cnx, int cny, int cnz,
+                                                          const int* __restrict__ rowmin,
+                                                          const int* __restrict__ rowmax, uint8_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n1) return;
+  const ParticleRec r = list[i];
+  const int c = cid[r.idx];
+  const int cx = c % cnx, cy = (c / cnx) % cny, cz = c / (cnx * cny);
+  bool extreme = false;
+  for (int oct = 0; oct < 8 && !extreme; ++oct) {
+    const int sx = (oct & 1) ? 1 : -1, sy = (oct & 2) ? 1 : -1, sz = (oct & 4) ? 1 : -1;
+    bool found = false;
+    int budget = kRefineBudget;
+    for (int z2 = cz; z2 >= 0 && z2 < cnz && !found && budget > 0; z2 += sz) {
+      for (int y2 = cy; y2 >= 0 && y2 < cny && !found && budget > 0; y2 += sy) {
+        --budget;
+        const int row = z2 * cny + y2;
+        if (sx > 0 ? rowmax[row] < cx : rowmin[row] > cx) continue;  // no occupied cell on that side
+        const int64_t rowbase = (int64_t)row * cnx;
+        const int a = sx > 0 ? cell_start[rowbase + cx] : cell_start[rowbase];
+        const int b = sx > 0 ? cell_start[rowbase + cnx] : cell_start[rowbase + cx + 1];
+        // nearest cells first: ascending records for +x, descending for -x
+        for (int j = 0; j < b - a && !found; ++j) {
+          const ParticleRec q = rec[sx > 0 ? a + j : b - 1 - j];
+          const double ex = q.x - r.x, ey = q.y - r.y, ez = q.z - r.z;
+          found = sx * ex >= 0.0 && sy * ey >= 0.0 && sz * ez >= 0.0 && (ex != 0.0 || ey != 0.0 || ez != 0.0);
+        }
+      }
+    }
+    if (!found) extreme = true;  // empty closed octant, or the budget ran out
+  }
+  keep[i] = extreme ? 1 : 0;
 }
 
 // bounding box (lo xyz, hi xyz) of every chunk of 32 list records
@@ -820,7 +895,7 @@ int ensure_hull_list(ptv_hash* h, cudaStream_t stream) {
   PTV_CUDA(cudaMemsetAsync(count, 0, sizeof(int), stream));
   hull_row_extent_kernel<<<(nrows + 127) / 128, 128, 0, stream>>>(h->cell_start, cnx, nrows, rowmin, rowmax);
   hull_dominance_kernel<<<1, 512, 0, stream>>>(cny, cnz, rowmin, rowmax, tmp, tab);
-  hull_compact_kernel<<<(unsigned)((nruns + 3) / 4), 128, 0, stream>>>(h->rec, h->cid, h->n, cnx, nrows, tab,
+  hull_compact_kernel<<<(unsigned)((nruns + 3) / 4), 128, 0, stream>>>(h->rec, h->cid, h->n, cnx, nrows, tab, nullptr,
                                                                       h->hull_rec, count);
   count_launches(3);
   PTV_CUDA(cudaGetLastError());
@@ -828,8 +903,35 @@ int ensure_hull_list(ptv_hash* h, cudaStream_t stream) {
   PTV_CUDA(cudaMemcpyAsync(&host, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
   PTV_CUDA(cudaStreamSynchronize(stream));
   h->hull_n = host;
+  h->hull_list = h->hull_rec;
+  if (host > 0 && tuning().hull >= 2) {
+    // stage 2: particle-level test on the survivors, compacted again (same chunk structure)
+    const int64_t nruns2 = ((int64_t)host + kHullRun - 1) / kHullRun;
+    const int64_t need2 = (int64_t)host + 32 * nruns2;
+    if (h->hull_cap2 < need2) {
+      cudaFree(h->hull_rec2);
+      cudaFree(h->hull_keep);
+      h->hull_rec2 = nullptr;
+      h->hull_keep = nullptr;
+      h->hull_cap2 = 0;
+      PTV_CUDA(cudaMalloc(&h->hull_rec2, (size_t)need2 * sizeof(ParticleRec)));
+      PTV_CUDA(cudaMalloc(&h->hull_keep, (size_t)need2));
+      h->hull_cap2 = need2;
+    }
+    PTV_CUDA(cudaMemsetAsync(count, 0, sizeof(int), stream));
+    hull_refine_kernel<<<(host + 127) / 128, 128, 0, stream>>>(h->hull_rec, host, h->rec, h->cell_start, h->cid, cnx, cny,
+                                                             cnz, rowmin, rowmax, h->hull_keep);
+    hull_compact_kernel<<<(unsigned)((nruns2 + 3) / 4), 128, 0, stream>>>(h->hull_rec, h->cid, host, cnx, nrows, tab,
+                                                                         h->hull_keep, h->hull_rec2, count);
+    count_launches(2);
+    PTV_CUDA(cudaGetLastError());
+    PTV_CUDA(cudaMemcpyAsync(&host, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PTV_CUDA(cudaStreamSynchronize(stream));
+    h->hull_n = host;
+    h->hull_list = h->hull_rec2;
+  }
   if (host > 0) {
-    hull_box_kernel<<<(host / 32 + 3) / 4, 128, 0, stream>>>(h->hull_rec, host / 32, h->hull_box);
+    hull_box_kernel<<<(host / 32 + 3) / 4, 128, 0, stream>>>(h->hull_list, host / 32, h->hull_box);
     count_launches(1);
     PTV_CUDA(cudaGetLastError());
   }

@@ -374,6 +374,8 @@ extern "C" int ptv_hash_destroy(ptv_hash* h) {
   cudaFree(h->fail_count);
   cudaFree(h->hull_rec);
   cudaFree(h->hull_box);
+  cudaFree(h->hull_rec2);
+  cudaFree(h->hull_keep);
   cudaFree(h->hull_tab);
   if (h->bbox_host) cudaFreeHost(h->bbox_host);
   if (h->err_host) cudaFreeHost(h->err_host);

@@ -65,7 +65,7 @@ static int run_linear(ptv_hash* h, KnnParams& p, bool f32, cudaStream_t stream) 
   if (tuning().hull != 0) {
     rc = ensure_hull_list(h, stream);
     if (rc != PTV_OK) return rc;
-    p.hull_rec = h->hull_rec;
+    p.hull_rec = h->hull_list;
     p.hull_box = h->hull_box;
     p.hull_n = h->hull_n;
   }

@@ -46,7 +46,7 @@ struct Tuning {
   int stats = 0;     // 1 = count streamed tiles
   int linear_k = 64;   // method='linear': the first candidate radius is the one expected to hold this many particles (2.5 spacings)
   int linear_occ = 4;  // method='linear': CTAs per SM the kernel is compiled for (3: 168 registers, 4: 128 + spills)
-  int hull = 1;      // method='linear': 1 = decide hull membership on the hull-candidate list, 0 = scan all particles
+  int hull = 2;      // method='linear': hull membership decided on the hull-candidate list (2: cell + particle dominance, 1: cell dominance only), 0 = scan all particles
   double rscale = 1.3;  // stream kernel: first scan radius^2 = rscale * r_est^2
 };
 Tuning& tuning();
@@ -79,7 +79,11 @@ struct ptv_hash {
   int64_t fail_cap = 0;
   unsigned long long* fail_count = nullptr;  // [0] low 32 bits: fail count; [1]: streamed tiles (stats)
   // method='linear': hull-candidate records and the dominance tables they come from (built on demand)
-  ptv::ParticleRec* hull_rec = nullptr;
+  ptv::ParticleRec* hull_rec = nullptr;   // stage 1: particles of undominated cells
+  ptv::ParticleRec* hull_rec2 = nullptr;  // stage 2: particles with an empty closed octant
+  ptv::ParticleRec* hull_list = nullptr;  // the list the kernel uses (one of the two)
+  uint8_t* hull_keep = nullptr;
+  int64_t hull_cap2 = 0;
   double* hull_box = nullptr;
   int64_t hull_cap = 0;
   int* hull_tab = nullptr;

@@ -802,7 +802,7 @@ def _linear_case(g, tag):
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])
-@pytest.mark.parametrize("hull", [1, 0])
+@pytest.mark.parametrize("hull", [2, 1, 0])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_linear_golden(golden_dir, tag, hull, dtype):
     """The reference's default method against golden vectors of the unmodified reference: values within
@@ -816,7 +816,7 @@ def test_linear_golden(golden_dir, tag, hull, dtype):
                                                  return_knn=True)
         st = gi.default_engine().linear_stats()
     finally:
-        set_tuning(hull=1, stats=0)
+        set_tuning(hull=2, stats=0)
     assert U.dtype == dtype
     assert st["unresolved"] == 0
     assert np.array_equal(rows, g[tag + "_simplex"])
@@ -854,7 +854,7 @@ def test_linear_lattice_wall_particles_golden(golden_dir):
     assert np.abs(np.stack([Um, Vm, Wm])[:, m] - np.stack([U, V, W])[:, m]).max() <= 1e-11
 
 
-@pytest.mark.parametrize("hull", [1, 0])
+@pytest.mark.parametrize("hull", [2, 1, 0])
 def test_linear_sphere_pack_vs_oracle(hull):
     """Config-1-like sphere pack (96^3 grid, 40k vectors + lattice wall particles, pore mask): every pore
     voxel against scipy's Delaunay (simplex rows exact, values within tolerance); linear precision: a
@@ -875,7 +875,7 @@ def test_linear_sphere_pack_vs_oracle(hull):
                                                  out_dtype=np.float64, return_knn=True)
         st = gi.default_engine().linear_stats()
     finally:
-        set_tuning(hull=1, stats=0)
+        set_tuning(hull=2, stats=0)
     assert st["unresolved"] == 0
     og, _ = rp.create_grid(bounds, n)
     fc = rp.flat_coords(og)
