@@ -419,12 +419,44 @@ __device__ int finish_voxel(const KnnParams& p, WarpCache& wc, CandSet& cs, doub
   const double margin = 1e-6 * g.cell;
   if (!all_real(t)) {
     if (p.hull_rec == nullptr) return kVirtual;
+    const Tet local = t;
     cs.with_hull = true;
     const int rc = lp_run(p, cs, wc, t, qpx, qpy, qpz, pivots);
     cs.with_hull = false;
     if (rc != 0) return kFailed;
     if (!all_real(t)) return kOutside;  // the programme over a superset of the hull vertices is unbounded
+    // q is inside the hull, but the tetrahedron just found hangs on far-away extreme points: its sphere
+    // spans the cloud and verifying it would read everything.  Go back to the local answer and widen the
+    // ball around q (x1.6 per step) until the virtual vertices are gone -- they must go, q is inside.
+    const double r_loc = r_cov > 0.0 ? r_cov : 2.0 * g.cell;
+    {
+      Geo geo;
+      tet_geo(t, geo);
+      if (geo.cc <= 36.0 * r_loc * r_loc) goto verify;  // a sphere of the local scale: keep it
+    }
+    t = local;
+    TileGeom qg;
+    qg.lo[0] = qg.hi[0] = qx;
+    qg.lo[1] = qg.hi[1] = qy;
+    qg.lo[2] = qg.hi[2] = qz;
+    set_rmax(g, qg);
+    double rb = r_loc;
+    while (!all_real(t)) {
+      if (rb >= qg.rmax) return kFailed;  // cannot happen: the hull phase found a real tetrahedron
+      rb = fmin(1.6 * rb, qg.rmax);
+      CandSet bs;
+      bs.with_hull = false;
+      bs.tg = qg;
+      bs.rg = make_region(g, bs.tg, rb);
+      bs.n = warp_gather(g, bs.tg, bs.rg, wc);
+      clobbered = true;
+      if (bs.n >= 0) set_query(wc, bs.n, qpx, qpy, qpz);
+      else stat_add(p, 3, 1);
+      if (lp_run(p, bs, wc, t, qpx, qpy, qpz, pivots) != 0) return kFailed;
+    }
+    r_cov = rb;  // converged on a set covering B(q, rb)
   }
+verify:
   bool first = true;
   for (;;) {
     Geo geo;
@@ -607,7 +639,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) delaunay_linear_kernel(const 
               } else {
                 bool clobbered = false;
                 ++general;
-                rc = finish_voxel(p, wc, cs, x, y, z, xp, yp, zp, 0.0, tet, pivots, clobbered);
+                rc = finish_voxel(p, wc, cs, x, y, z, xp, yp, zp, R, tet, pivots, clobbered);
                 if (clobbered) cs.n = warp_gather(g, cs.tg, cs.rg, wc);
               }
             } else {
