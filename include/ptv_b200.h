@@ -68,7 +68,10 @@ const char* ptv_last_error(void);
 int ptv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 /* Tuning knobs for experiments ("ppc" particles per cell, "r0" rings merged into the first
  * staging batch, "tile" / "stream_tile" 32|64|128 threads per voxel tile of the heap / streaming
- * kernel, "stream" 0|1 use the streaming kernel, "stats" 0|1).  Unknown key -> PTV_ERR_INVALID. */
+ * kernel, "stream" 0|1 use the streaming kernel, "stats" 0|1, "rscale" first-radius factor of the
+ * streaming kernel; method='linear': "hull" 2|1|0 hull-candidate list with / without the particle-level
+ * stage / none (scan all particles), "linear_k" the first candidate radius holds this many particles,
+ * "linear_occ" 3|4 CTAs per SM).  Results never depend on them.  Unknown key -> PTV_ERR_INVALID. */
 int ptv_set_tuning(const char* key, double value);
 /* Number of CUDA kernels this library has launched in this process so far (bench.py's
  * gpu_launches is the difference across the timed region). */

@@ -7,21 +7,24 @@
 // inside, the one that holds q deepest (largest r^2 - |q-c|^2) is the circumsphere of that
 // tetrahedron (lifting map: the lower-hull facet under q).  One warp solves the programme for one
 // voxel by dual-simplex pivoting: start from a huge tetrahedron of four virtual points around q,
-// bring in the particle deepest inside the current circumsphere (all 32 lanes scan candidates), drop
-// the vertex picked by the ratio test that keeps q inside.  Candidates are the particles of the hash
-// cells within R of the voxel; the answer is accepted only when all four vertices are real and the
-// circumsphere lies inside the scanned region -- then no particle anywhere is inside it and the
-// tetrahedron is THE Delaunay tetrahedron of q, however it was found.  Otherwise R grows.
+// bring in a particle that lies inside the current circumsphere (all 32 lanes scan candidates; the one
+// with the largest violation per squared distance from q enters), drop the vertex picked by the ratio
+// test that keeps q inside.  Every pivot raises the objective and keeps q inside, whatever set the
+// entering particle was drawn from, so the search may look anywhere; the answer is accepted only when
+// all four vertices are real and the cells its circumsphere touches were scanned without a violator --
+// then no particle anywhere is inside it and the tetrahedron is THE Delaunay tetrahedron of q, however
+// it was found.
 //
 //   * a warp owns an 8x4 row block of a tile: the candidates within R of the block are gathered once
 //     into shared memory (structure of arrays, lane j reads element j: conflict-free) and serve all 32
-//     voxels; a voxel that falls inside the previous voxel's tetrahedron re-uses it without a search;
-//   * voxels the shared pass cannot finish (near the hull, in voids) go through solve_general: region
-//     of the voxel alone, growing radius, candidates from shared memory or straight from global memory;
+//     voxels; a voxel that falls inside the previous voxel's tetrahedron re-uses it without a search,
+//     otherwise that tetrahedron's vertices seed the programme (lp_seed);
+//   * voxels whose sphere leaves the gathered region (next to grains, near the hull) are finished inline
+//     by finish_voxel: scan the cells the sphere touches, pivot, repeat until a scan finds nothing;
 //   * outside the hull the programme is unbounded: the virtual vertices never leave.  To decide that
-//     without scanning all particles, the final level uses region(R) U H, H = the particles that are
-//     not dominated in all eight octants by occupied hash cells (every hull vertex is in H, see
-//     hull_compact_kernel), a few thousand records.
+//     without scanning all particles the programme is re-run on cache U H, H = a superset of the cloud's
+//     extreme points built once per hash (ensure_hull_list: cell-level then particle-level octant
+//     dominance; ~2000 records for 10M particles, in chunks of 32 with bounding boxes);
 //   * q is nudged by 2^-36 of its distance towards an interior point of the cloud before the search, so
 //     a voxel lying exactly on a face of the triangulation (lattice wall particles, main.py:173-178) or
 //     on the hull is not a degenerate programme; the weights are computed for the unmoved q.
