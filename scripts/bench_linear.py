@@ -39,6 +39,18 @@ for name in names:
     pore = int(cfg["mask"].sum())
     out[f"linear_{name}"] = {"grid": n, "particles": int(cfg["points"].shape[0]), "pore_voxels": pore, "ms": best, "first_call_ms": first,
                              "pore_voxels_per_s": pore / best * 1e3, "stats": eng.linear_stats()}
+    if n <= 256:  # the same through the drop-in API: host DataFrame in, host arrays out (wall clock)
+        import time
+        import numpy as np
+        import pandas as pd
+        from ptv_interpolation_b200 import interpolator as gi
+        p_h, v_h, m_h = cfg["points"].cpu().numpy(), cfg["values"].cpu().numpy(), cfg["mask"].cpu().numpy()
+        df = pd.DataFrame({"x": p_h[:, 0], "y": p_h[:, 1], "z": p_h[:, 2], "u": v_h[:, 0], "v": v_h[:, 1], "w": v_h[:, 2]})
+        grid, _ = gi.create_grid(((0, n), (0, n), (0, n)), n)
+        gi.interpolate_field(df, grid, method="linear", mask=m_h)
+        t0 = time.perf_counter()
+        gi.interpolate_field(df, grid, method="linear", mask=m_h)
+        out[f"linear_{name}"]["e2e_interpolate_field_ms"] = (time.perf_counter() - t0) * 1e3
     print(name, out[f"linear_{name}"], file=sys.stderr, flush=True)
     del cfg, mask, res
 print(json.dumps(out))
