@@ -38,6 +38,14 @@ def test_error_mapping():
         _cabi.check(_cabi.PTV_ERR_SINGULAR)
     with pytest.raises(_cabi.PTVError):
         _cabi.check(_cabi.PTV_ERR_CUDA)
+    from scipy.spatial import QhullError
+    with pytest.raises(QhullError):  # method='linear': what griddata raises from Qhull
+        _cabi.check(_cabi.PTV_ERR_QHULL)
+    # the numeric codes are the header's
+    hdr = open(os.path.join(ROOT, "include", "ptv_b200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define (PTV_[A-Z0-9_]+) (\d+)", hdr)}
+    assert defs["PTV_METHOD_LINEAR"] == _cabi.METHOD_LINEAR and defs["PTV_ERR_QHULL"] == _cabi.PTV_ERR_QHULL
+    assert defs["PTV_METHOD_IDW"] == _cabi.METHOD_IDW and defs["PTV_METHOD_RBF_QUINTIC"] == _cabi.METHOD_RBF_QUINTIC
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -49,6 +57,10 @@ def test_no_cpu_fallback_without_gpu():
     grid, _ = gi.create_grid(((0, 4), (0, 4), (0, 4)), 4)
     with pytest.raises(_cabi.PTVError):
         gi.interpolate_field(df, grid, method="idw", idw_neighbors=5)
+    with pytest.raises(_cabi.PTVError):  # the reference's default method has no CPU path either
+        gi.interpolate_field(df, grid)
+    with pytest.raises(ValueError):  # griddata's own error for 3-D 'cubic' (interpolator.py:197)
+        gi.interpolate_field(df, grid, method="cubic")
     from ptv_interpolation_b200 import physics
     with pytest.raises(_cabi.PTVError):
         physics.compute_consistent_divergence(*(np.zeros((3, 3, 3)),) * 3, np.ones((3, 3, 3), bool), 1, 1, 1)
