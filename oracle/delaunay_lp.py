@@ -13,7 +13,10 @@ around q, repeatedly bring in the point deepest inside the current circumsphere 
 chosen by the ratio test that keeps q inside.  ``tests/test_oracle_golden.py`` checks it against
 ``scipy.spatial.Delaunay.find_simplex`` and against golden vectors of the unmodified reference.
 
-The CUDA kernel (csrc/delaunay_linear.cu) follows the same programme, restricted to hash cells.
+The CUDA kernel (csrc/delaunay_linear.cu) solves the same programme restricted to hash cells.  It picks
+the entering point by violation per squared distance from q instead of the deepest one; the choice only
+changes the path, not the optimum (every pivot raises the objective, the optimum is unique for points in
+general position), which is why this restatement can keep the textbook rule.
 """
 from __future__ import annotations
 

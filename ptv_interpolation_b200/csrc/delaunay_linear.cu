@@ -38,7 +38,7 @@
 namespace ptv {
 namespace {
 
-constexpr int kCap = 416;         // cached candidates per warp (32 B each): 4 CTAs of 4 warps per SM
+constexpr int kCap = 416;         // cached candidates per warp (32 B each, 53 KB per CTA)
 constexpr int kMaxPivots = 600;
 constexpr double kEta = 1.0 / 68719476736.0;  // 2^-36
 constexpr unsigned kFull = 0xffffffffu;
@@ -422,27 +422,28 @@ __device__ int finish_voxel(const KnnParams& p, WarpCache& wc, CandSet& cs, doub
   const double margin = 1e-6 * g.cell;
   if (!all_real(t)) {
     if (p.hull_rec == nullptr) return kVirtual;
-    const Tet local = t;
     cs.with_hull = true;
     const int rc = lp_run(p, cs, wc, t, qpx, qpy, qpz, pivots);
     cs.with_hull = false;
     if (rc != 0) return kFailed;
     if (!all_real(t)) return kOutside;  // the programme over a superset of the hull vertices is unbounded
     // q is inside the hull, but the tetrahedron just found hangs on far-away extreme points: its sphere
-    // spans the cloud and verifying it would read everything.  Go back to the local answer and widen the
-    // ball around q (x1.6 per step) until the virtual vertices are gone -- they must go, q is inside.
+    // spans the cloud and verifying it would read everything.  Start again from the virtual tetrahedron and
+    // widen the ball around q (x1.6 per step) until the virtual vertices are gone -- they must go, q is
+    // inside.  (Restarting costs a few pivots on rare voxels; keeping a copy of the local tetrahedron alive
+    // across the hull phase costs every voxel registers.)
     const double r_loc = r_cov > 0.0 ? r_cov : 2.0 * g.cell;
     {
       Geo geo;
       tet_geo(t, geo);
       if (geo.cc <= 36.0 * r_loc * r_loc) goto verify;  // a sphere of the local scale: keep it
     }
-    t = local;
     TileGeom qg;
     qg.lo[0] = qg.hi[0] = qx;
     qg.lo[1] = qg.hi[1] = qy;
     qg.lo[2] = qg.hi[2] = qz;
     set_rmax(g, qg);
+    init_virtual(t, qx, qy, qz, 1e4 * qg.rmax);
     double rb = r_loc;
     while (!all_real(t)) {
       if (rb >= qg.rmax) return kFailed;  // cannot happen: the hull phase found a real tetrahedron

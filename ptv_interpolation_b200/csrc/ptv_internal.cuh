@@ -45,7 +45,7 @@ struct Tuning {
   int stream_tile = 128;
   int stats = 0;     // 1 = count streamed tiles
   int linear_k = 64;   // method='linear': the first candidate radius is the one expected to hold this many particles (2.5 spacings)
-  int linear_occ = 4;  // method='linear': CTAs per SM the kernel is compiled for (3: 168 registers, 4: 128 + spills)
+  int linear_occ = 3;  // method='linear': CTAs per SM the kernel is compiled for (3: 168 registers, 4: 128 + spills)
   int hull = 2;      // method='linear': hull membership decided on the hull-candidate list (2: cell + particle dominance, 1: cell dominance only), 0 = scan all particles
   double rscale = 1.3;  // stream kernel: first scan radius^2 = rscale * r_est^2
 };
