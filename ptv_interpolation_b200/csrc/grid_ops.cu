@@ -347,14 +347,51 @@ __device__ __forceinline__ void ld4(const Tf* __restrict__ p, double (&o)[4]) {
 template <typename Tf>
 struct Grad4 { double dx[4], dy[4], dz[4]; };
 
+// The 7-point neighbourhood of 4 consecutive x as raw loads.  All of a thread's loads (3 fields x 5 vectors
+// + 2 scalars, and the mask) are issued before anything is converted or tested, so a thread has ~330 B in
+// flight instead of walking mask -> field -> field -> field latency by latency.
+template <typename Tf> struct Raw4 { Tf v[4]; };
 template <typename Tf>
-__device__ __forceinline__ Grad4<Tf> gradients4(const Tf* __restrict__ f, int64_t i, int x, int y, int z, int nx, int ny,
-                                                int nz, const Divisors6& dv) {
+__device__ __forceinline__ Raw4<Tf> ldraw4(const Tf* __restrict__ p) {
+  // volatile asm: the compiler must not sink the loads below the mask test that follows them
+  Raw4<Tf> r;
+  if (sizeof(Tf) == 4) {
+    float a, b, c, d;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p));
+    r.v[0] = (Tf)a; r.v[1] = (Tf)b; r.v[2] = (Tf)c; r.v[3] = (Tf)d;
+  } else {
+    double a, b, c, d;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(d) : "l"(p + 2));
+    r.v[0] = (Tf)a; r.v[1] = (Tf)b; r.v[2] = (Tf)c; r.v[3] = (Tf)d;
+  }
+  return r;
+}
+template <typename Tf> struct Stencil4 { Raw4<Tf> c, ym, yp, zm, zp; Tf xl, xr; };
+
+template <typename Tf>
+__device__ __forceinline__ Stencil4<Tf> load_stencil4(const Tf* __restrict__ f, int64_t i, int x, int y, int z, int nx,
+                                                     int ny, int nz) {
   const int64_t sy = nx, sz = (int64_t)nx * ny;
-  double e[6], c[4], a[4], b[4];
-  ld4(f + i, c);
-  e[0] = x > 0 ? (double)f[i - 1] : 0.0;
-  e[5] = x + 4 < nx ? (double)f[i + 4] : 0.0;
+  Stencil4<Tf> s;
+  s.c = ldraw4(f + i);
+  s.ym = ldraw4(f + (y > 0 ? i - sy : i));       // (edge rows re-read the centre: unused below)
+  s.yp = ldraw4(f + (y < ny - 1 ? i + sy : i));
+  s.zm = ldraw4(f + (z > 0 ? i - sz : i));
+  s.zp = ldraw4(f + (z < nz - 1 ? i + sz : i));
+  s.xl = __ldg(f + (x > 0 ? i - 1 : i));
+  s.xr = __ldg(f + (x + 4 < nx ? i + 4 : i));
+  return s;
+}
+
+template <typename Tf>
+__device__ __forceinline__ Grad4<Tf> gradients4(const Stencil4<Tf>& s, int x, int y, int z, int nx, int ny, int nz,
+                                                const Divisors6& dv) {
+  double e[6], c[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c[j] = (double)s.c.v[j];
+  e[0] = (double)s.xl;
+  e[5] = (double)s.xr;
 #pragma unroll
   for (int j = 0; j < 4; ++j) e[j + 1] = c[j];
   Grad4<Tf> g;
@@ -365,12 +402,20 @@ __device__ __forceinline__ Grad4<Tf> gradients4(const Tf* __restrict__ f, int64_
     else if (pos == nx - 1) g.dx[j] = grad_div(__dsub_rn(e[j + 1], e[j]), dv.d[0]);
     else g.dx[j] = grad_div(__dsub_rn(e[j + 2], e[j]), dv.d[1]);
   }
-  if (y == 0) { ld4(f + i + sy, b); for (int j = 0; j < 4; ++j) g.dy[j] = grad_div(__dsub_rn(b[j], c[j]), dv.d[2]); }
-  else if (y == ny - 1) { ld4(f + i - sy, a); for (int j = 0; j < 4; ++j) g.dy[j] = grad_div(__dsub_rn(c[j], a[j]), dv.d[2]); }
-  else { ld4(f + i - sy, a); ld4(f + i + sy, b); for (int j = 0; j < 4; ++j) g.dy[j] = grad_div(__dsub_rn(b[j], a[j]), dv.d[3]); }
-  if (z == 0) { ld4(f + i + sz, b); for (int j = 0; j < 4; ++j) g.dz[j] = grad_div(__dsub_rn(b[j], c[j]), dv.d[4]); }
-  else if (z == nz - 1) { ld4(f + i - sz, a); for (int j = 0; j < 4; ++j) g.dz[j] = grad_div(__dsub_rn(c[j], a[j]), dv.d[4]); }
-  else { ld4(f + i - sz, a); ld4(f + i + sz, b); for (int j = 0; j < 4; ++j) g.dz[j] = grad_div(__dsub_rn(b[j], a[j]), dv.d[5]); }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double a = (double)s.ym.v[j], b = (double)s.yp.v[j];
+    if (y == 0) g.dy[j] = grad_div(__dsub_rn(b, c[j]), dv.d[2]);
+    else if (y == ny - 1) g.dy[j] = grad_div(__dsub_rn(c[j], a), dv.d[2]);
+    else g.dy[j] = grad_div(__dsub_rn(b, a), dv.d[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double a = (double)s.zm.v[j], b = (double)s.zp.v[j];
+    if (z == 0) g.dz[j] = grad_div(__dsub_rn(b, c[j]), dv.d[4]);
+    else if (z == nz - 1) g.dz[j] = grad_div(__dsub_rn(c[j], a), dv.d[4]);
+    else g.dz[j] = grad_div(__dsub_rn(b, a), dv.d[5]);
+  }
   return g;
 }
 
@@ -388,13 +433,16 @@ __global__ void __launch_bounds__(256) strain_vorticity_vec4_kernel(const Tf* __
   const int y = (int)(row % ny), z = (int)(row / ny);
   const int64_t i = row * nx + x;
   uchar4 m = make_uchar4(1, 1, 1, 1);
-  if (mask != nullptr) m = *reinterpret_cast<const uchar4*>(mask + i);
+  if (mask != nullptr) m = __ldg(reinterpret_cast<const uchar4*>(mask + i));
+  const Stencil4<Tf> su = load_stencil4(u, i, x, y, z, nx, ny, nz);
+  const Stencil4<Tf> sv = load_stencil4(v, i, x, y, z, nx, ny, nz);
+  const Stencil4<Tf> sw = load_stencil4(w, i, x, y, z, nx, ny, nz);
   const bool mk[4] = {m.x != 0, m.y != 0, m.z != 0, m.w != 0};
   double so[4] = {0.0, 0.0, 0.0, 0.0}, vo[4] = {0.0, 0.0, 0.0, 0.0};
   if (mk[0] || mk[1] || mk[2] || mk[3]) {
-    const Grad4<Tf> gu = gradients4(u, i, x, y, z, nx, ny, nz, dv6);
-    const Grad4<Tf> gv = gradients4(v, i, x, y, z, nx, ny, nz, dv6);
-    const Grad4<Tf> gw = gradients4(w, i, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gu = gradients4(su, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gv = gradients4(sv, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gw = gradients4(sw, x, y, z, nx, ny, nz, dv6);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (!mk[j]) continue;
