@@ -58,6 +58,14 @@ static int linear_check(int64_t n) {
 
 // method='linear': hull-candidate list (once per hash build), statistics slots, one launch
 static int run_linear(ptv_hash* h, KnnParams& p, bool f32, cudaStream_t stream) {
+  // a cloud without extent along an axis has no tetrahedra: Qhull stops with QH6154 (coplanar / collinear input)
+  for (int c = 0; c < 3; ++c) {
+    if (h->bbox_host[3 + c] - h->bbox_host[c] == 0.0) {
+      set_error("QH6154 Qhull precision error: Initial simplex is flat (the particles have no extent along axis " +
+                std::to_string(c) + ")");
+      return PTV_ERR_QHULL;
+    }
+  }
   int rc = ensure_fail_buffers(h, 0);
   if (rc != PTV_OK) return rc;
   PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, 8 * sizeof(unsigned long long), stream));

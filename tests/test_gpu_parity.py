@@ -722,6 +722,18 @@ def test_degenerate_grids_and_clouds(res):
             # differs from an extended-precision evaluation by 7e-6): compare that one case at 1e-3.
             tol = 1e-3 if (name == "collinear" and method == "sibson") else TOL
             _assert_vel(np.stack([U, V, W]), np.nan_to_num(np.stack([Ur, Vr, Wr])), vals, tol=tol)
+        # method='linear': a cloud with volume interpolates (outside the hull: 0); flat clouds have no
+        # tetrahedra and Qhull says so (QH6154) -- same exception type here
+        from scipy.spatial import QhullError
+        if name == "random":
+            U, V, W = gi.interpolate_field(_df(pts, vals), grid, method="linear", out_dtype=np.float64)
+            Ur, Vr, Wr = rp.interpolate_field(pts, vals, og, method="linear")
+            _assert_vel(np.stack([U, V, W]), np.stack([Ur, Vr, Wr]), vals)
+        else:
+            with pytest.raises(QhullError):
+                rp.interpolate_field(pts, vals, og, method="linear")
+            with pytest.raises(QhullError):
+                gi.interpolate_field(_df(pts, vals), grid, method="linear")
     same = np.full((60, 3), 3.0)
     vals = rng.normal(size=(60, 3))
     U, V, W = gi.interpolate_field(_df(same, vals), grid, method="idw", idw_neighbors=10, out_dtype=np.float64)
