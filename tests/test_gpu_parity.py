@@ -934,3 +934,48 @@ def test_linear_scattered_points_duplicates_and_errors():
         o2, _ = rp.create_grid(((0.5, 12.5), (0.5, 12.5), (0.5, 12.5)), r)
         U, V, W = gi.interpolate_field(_df(p2, v2), g2, method="linear", out_dtype=np.float64)
         _assert_vel(np.stack([U, V, W]), np.stack(rp.interpolate_field(p2, v2, o2, method="linear")), v2)
+
+
+@pytest.mark.parametrize("case", ["quasi2d", "offset", "clustered"])
+def test_linear_anisotropic_offset_and_clustered_clouds(case):
+    """Shapes that stress the search rather than the arithmetic: the quasi-2-D slab of generate_cylinders.py
+    (size x size/2 x 16), a cloud far from the origin, and a cloud whose density varies by 1000x."""
+    rng = np.random.default_rng({"quasi2d": 1, "offset": 2, "clustered": 3}[case])
+    if case == "quasi2d":
+        pts = rng.uniform([0, 0, 0], [64, 32, 4], size=(20000, 3))
+        b, res = ((0, 65), (0, 33), (0, 5)), (40, 20, 5)
+    elif case == "offset":
+        off = np.array([1.0e4, -2.0e4, 3.0e4])
+        pts = rng.uniform(0, 20, size=(8000, 3)) + off
+        b = tuple((float(o) + 1.0, float(o) + 20.0) for o in off)
+        res = (17, 16, 15)
+    else:
+        dense = rng.normal([6, 6, 6], 0.4, size=(15000, 3))
+        sparse = rng.uniform(0, 24, size=(1500, 3))
+        pts = np.concatenate([dense, sparse])
+        b, res = ((0, 25), (0, 25), (0, 25)), (24, 23, 22)
+    vals = np.stack([np.sin(0.3 * pts[:, 0]), 0.1 * pts[:, 1], np.cos(0.2 * pts[:, 2])], -1) - 0.5
+    grid, _ = gi.create_grid(b, res)
+    og, _ = rp.create_grid(b, res)
+    set_tuning(stats=1)
+    try:
+        U, V, W, bw, rows = gi.interpolate_field(_df(pts, vals), grid, method="linear", out_dtype=np.float64,
+                                                 return_knn=True)
+        st = gi.default_engine().linear_stats()
+    finally:
+        set_tuning(stats=0)
+    assert st["unresolved"] == 0
+    if case == "offset":
+        # Qhull works on absolute coordinates: 3e4 away from the origin its own answer moves (one voxel of
+        # this grid changes by 5.5e-4 against the same cloud shifted back -- the SciPy-free restatement
+        # oracle/delaunay_lp.py sides with the shifted-back answer to 1e-16).  The kernel works on differences
+        # and is translation invariant, so it is compared with the reference on the shifted-back problem.
+        pts_r, og_r = pts - off, tuple(a - o for a, o in zip(og, off))
+        assert np.array_equal(pts_r + off, pts)
+    else:
+        pts_r, og_r = pts, og
+    ref = np.stack(rp.interpolate_field(pts_r, vals, og_r, method="linear"))
+    _assert_vel(np.stack([U, V, W]), ref, vals)
+    ref_rows, _ = rp.delaunay_simplex_rows(pts_r, rp.flat_coords(og_r))
+    assert (rows == ref_rows).all(1).mean() >= 0.999
+    assert np.array_equal(rows[:, 0] < 0, ref_rows[:, 0] < 0)  # the same voxels lie outside the hull
