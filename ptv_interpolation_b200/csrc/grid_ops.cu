@@ -280,6 +280,13 @@ __device__ __forceinline__ double grad_div(double num, const Divisor& d) {
   return __ddiv_rn(num, d.den);
 }
 
+// kPow2: every divisor of the launch is a power of two (unit or power-of-two spacing): the run-time tests go
+template <bool kPow2>
+__device__ __forceinline__ double grad_div_t(double num, const Divisor& d) {
+  if (kPow2) return __dmul_rn(num, d.inv);
+  return grad_div(num, d);
+}
+
 struct Divisors6 { Divisor d[6]; };
 
 template <typename Tf>
@@ -384,7 +391,7 @@ __device__ __forceinline__ Stencil4<Tf> load_stencil4(const Tf* __restrict__ f, 
   return s;
 }
 
-template <typename Tf>
+template <typename Tf, bool kPow2>
 __device__ __forceinline__ Grad4<Tf> gradients4(const Stencil4<Tf>& s, int x, int y, int z, int nx, int ny, int nz,
                                                 const Divisors6& dv) {
   double e[6], c[4];
@@ -398,28 +405,28 @@ __device__ __forceinline__ Grad4<Tf> gradients4(const Stencil4<Tf>& s, int x, in
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int pos = x + j;
-    if (pos == 0) g.dx[j] = grad_div(__dsub_rn(e[j + 2], e[j + 1]), dv.d[0]);
-    else if (pos == nx - 1) g.dx[j] = grad_div(__dsub_rn(e[j + 1], e[j]), dv.d[0]);
-    else g.dx[j] = grad_div(__dsub_rn(e[j + 2], e[j]), dv.d[1]);
+    if (pos == 0) g.dx[j] = grad_div_t<kPow2>(__dsub_rn(e[j + 2], e[j + 1]), dv.d[0]);
+    else if (pos == nx - 1) g.dx[j] = grad_div_t<kPow2>(__dsub_rn(e[j + 1], e[j]), dv.d[0]);
+    else g.dx[j] = grad_div_t<kPow2>(__dsub_rn(e[j + 2], e[j]), dv.d[1]);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const double a = (double)s.ym.v[j], b = (double)s.yp.v[j];
-    if (y == 0) g.dy[j] = grad_div(__dsub_rn(b, c[j]), dv.d[2]);
-    else if (y == ny - 1) g.dy[j] = grad_div(__dsub_rn(c[j], a), dv.d[2]);
-    else g.dy[j] = grad_div(__dsub_rn(b, a), dv.d[3]);
+    if (y == 0) g.dy[j] = grad_div_t<kPow2>(__dsub_rn(b, c[j]), dv.d[2]);
+    else if (y == ny - 1) g.dy[j] = grad_div_t<kPow2>(__dsub_rn(c[j], a), dv.d[2]);
+    else g.dy[j] = grad_div_t<kPow2>(__dsub_rn(b, a), dv.d[3]);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const double a = (double)s.zm.v[j], b = (double)s.zp.v[j];
-    if (z == 0) g.dz[j] = grad_div(__dsub_rn(b, c[j]), dv.d[4]);
-    else if (z == nz - 1) g.dz[j] = grad_div(__dsub_rn(c[j], a), dv.d[4]);
-    else g.dz[j] = grad_div(__dsub_rn(b, a), dv.d[5]);
+    if (z == 0) g.dz[j] = grad_div_t<kPow2>(__dsub_rn(b, c[j]), dv.d[4]);
+    else if (z == nz - 1) g.dz[j] = grad_div_t<kPow2>(__dsub_rn(c[j], a), dv.d[4]);
+    else g.dz[j] = grad_div_t<kPow2>(__dsub_rn(b, a), dv.d[5]);
   }
   return g;
 }
 
-template <typename Tf>
+template <typename Tf, bool kPow2>
 __global__ void __launch_bounds__(256) strain_vorticity_vec4_kernel(const Tf* __restrict__ u, const Tf* __restrict__ v,
                                                                      const Tf* __restrict__ w,
                                                                      const uint8_t* __restrict__ mask, int nx, int ny,
@@ -440,9 +447,9 @@ __global__ void __launch_bounds__(256) strain_vorticity_vec4_kernel(const Tf* __
   const bool mk[4] = {m.x != 0, m.y != 0, m.z != 0, m.w != 0};
   double so[4] = {0.0, 0.0, 0.0, 0.0}, vo[4] = {0.0, 0.0, 0.0, 0.0};
   if (mk[0] || mk[1] || mk[2] || mk[3]) {
-    const Grad4<Tf> gu = gradients4(su, x, y, z, nx, ny, nz, dv6);
-    const Grad4<Tf> gv = gradients4(sv, x, y, z, nx, ny, nz, dv6);
-    const Grad4<Tf> gw = gradients4(sw, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gu = gradients4<Tf, kPow2>(su, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gv = gradients4<Tf, kPow2>(sv, x, y, z, nx, ny, nz, dv6);
+    const Grad4<Tf> gw = gradients4<Tf, kPow2>(sw, x, y, z, nx, ny, nz, dv6);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (!mk[j]) continue;
@@ -495,14 +502,17 @@ extern "C" int ptv_strain_vorticity(const void* d_u, const void* d_v, const void
   const bool vec = (nx % 4 == 0) && al16(d_u) && al16(d_v) && al16(d_w) && al16(d_strain) && al16(d_vorticity) &&
                    (d_mask == nullptr || (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0);
   const unsigned nbv = (unsigned)((n / 4 + 255) / 256);
-  if (vec && dtype == PTV_F32)
-    strain_vorticity_vec4_kernel<float><<<nbv, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dv6, (float*)d_strain,
-        (float*)d_vorticity);
-  else if (vec && dtype == PTV_F64)
-    strain_vorticity_vec4_kernel<double><<<nbv, 256, 0, (cudaStream_t)stream>>>(
-        (const double*)d_u, (const double*)d_v, (const double*)d_w, d_mask, nx, ny, nz, dv6, (double*)d_strain,
-        (double*)d_vorticity);
+  bool pow2 = true;
+  for (int c = 0; c < 6; ++c) pow2 = pow2 && dv6.d[c].pow2;
+#define PTV_SV4(T, P2)                                                                                        \
+  strain_vorticity_vec4_kernel<T, P2><<<nbv, 256, 0, (cudaStream_t)stream>>>(                                \
+      (const T*)d_u, (const T*)d_v, (const T*)d_w, d_mask, nx, ny, nz, dv6, (T*)d_strain, (T*)d_vorticity)
+  if (vec && dtype == PTV_F32) {
+    if (pow2) PTV_SV4(float, true); else PTV_SV4(float, false);
+  } else if (vec && dtype == PTV_F64) {
+    if (pow2) PTV_SV4(double, true); else PTV_SV4(double, false);
+  }
+#undef PTV_SV4
   else if (dtype == PTV_F32)
     strain_vorticity_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(
         (const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dv6, (float*)d_strain,
