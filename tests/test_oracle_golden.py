@@ -211,3 +211,29 @@ def test_linear_programme_restatement_matches_reference(golden_dir):
     q = fc[sel] + 2.0 ** -36 * (ctr - fc[sel])  # the kernel's nudge off the lattice planes
     out, _ = linear_interpolate(cb["points"], cb["values"], q)
     assert np.abs(out - g["c_uvw"].reshape(3, -1).T[sel]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_linear_programme_restatement_vs_scipy_random_clouds(seed):
+    """The SciPy-free restatement against scipy.spatial.Delaunay on fresh clouds: queries inside, just
+    inside / outside the hull (on segments through hull vertices) and far outside."""
+    from scipy.spatial import Delaunay
+    from oracle.delaunay_lp import containing_simplex
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0, 5, size=(150, 3)) * np.array([1.0, 2.0, 0.5])  # anisotropic box
+    tri = Delaunay(pts)
+    hull_v = np.unique(tri.convex_hull)
+    ctr = pts.mean(0)
+    t = rng.uniform(0.9, 1.1, size=60)[:, None]
+    near = ctr + t * (pts[rng.choice(hull_v, 60)] - ctr)           # around the hull along rays from the centre
+    q = np.concatenate([rng.uniform(-1, 6, size=(80, 3)) * np.array([1.0, 2.0, 0.5]), near,
+                        rng.uniform(20, 30, size=(5, 3))])
+    s = tri.find_simplex(q)
+    for qi, si in zip(q, s):
+        ids, lam = containing_simplex(pts, qi)
+        if si < 0:
+            assert ids is None
+        else:
+            assert ids is not None and np.array_equal(ids, np.sort(tri.simplices[si]))
+            assert abs(lam.sum() - 1.0) <= 1e-12 and lam.min() >= -1e-9
+            assert np.abs(lam @ pts[ids] - qi).max() <= 1e-9
