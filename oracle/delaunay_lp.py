@@ -89,3 +89,21 @@ def linear_interpolate(points, values, queries, fill_value=0.0):
             simp[n] = ids
             out[n] = lam @ values[ids]
     return out, simp
+
+
+def extreme_point_candidates(points):
+    """Restatement of the rule behind the kernel's hull-candidate list (csrc/delaunay_linear.cu,
+    hull_refine_kernel): a point can be an extreme point of the cloud only if some CLOSED octant around it
+    holds no other point.  (If every closed octant {s_i (x_i' - x_i) >= 0} held another point, any direction n
+    would have n.(p' - p) >= 0 for the p' in the octant of sign(n), so p could not be strictly separated from
+    the rest, i.e. it lies in their hull.)  O(N^2), for tests: returns the boolean candidate mask."""
+    p = np.asarray(points, dtype=np.float64)
+    d = p[None, :, :] - p[:, None, :]                      # d[i, j] = p_j - p_i
+    distinct = np.any(d != 0.0, axis=2)
+    keep = np.zeros(len(p), dtype=bool)
+    for sx in (-1.0, 1.0):
+        for sy in (-1.0, 1.0):
+            for sz in (-1.0, 1.0):
+                inside = (sx * d[..., 0] >= 0) & (sy * d[..., 1] >= 0) & (sz * d[..., 2] >= 0) & distinct
+                keep |= ~inside.any(axis=1)
+    return keep

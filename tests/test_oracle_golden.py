@@ -237,3 +237,29 @@ def test_linear_programme_restatement_vs_scipy_random_clouds(seed):
             assert ids is not None and np.array_equal(ids, np.sort(tri.simplices[si]))
             assert abs(lam.sum() - 1.0) <= 1e-12 and lam.min() >= -1e-9
             assert np.abs(lam @ pts[ids] - qi).max() <= 1e-9
+
+
+@pytest.mark.parametrize("kind", ["random", "lattice_faces", "sphere_shell"])
+def test_hull_candidate_rule_keeps_every_hull_vertex(kind):
+    """The closed-octant rule that prunes the kernel's hull-candidate list never drops a vertex of the convex
+    hull (scipy.spatial.ConvexHull), also with co-planar lattice points on the faces, and prunes hard."""
+    from scipy.spatial import ConvexHull
+    from oracle.delaunay_lp import extreme_point_candidates
+    rng = np.random.default_rng(5)
+    if kind == "random":
+        pts = rng.uniform(0, 10, size=(1500, 3))
+    elif kind == "lattice_faces":
+        g = np.arange(0, 9.0)
+        face = np.array([(x, y, 0.0) for x in g for y in g] + [(x, y, 8.0) for x in g for y in g]
+                        + [(0.0, y, z) for y in g for z in g] + [(8.0, y, z) for y in g for z in g])
+        pts = np.concatenate([np.unique(face, axis=0), rng.uniform(0.5, 7.5, size=(600, 3))])
+    else:
+        v = rng.normal(size=(800, 3))
+        pts = np.concatenate([5.0 * v / np.linalg.norm(v, axis=1, keepdims=True), rng.uniform(-2, 2, size=(400, 3))])
+    keep = extreme_point_candidates(pts)
+    hull = np.unique(ConvexHull(pts).vertices)
+    assert keep[hull].all()
+    if kind == "random":
+        assert keep.sum() <= 0.2 * len(pts)
+    if kind == "lattice_faces":  # the interior of the flat faces goes, only their outline can stay
+        assert keep.sum() <= 8 * 9 + 40
