@@ -101,9 +101,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    # build() returns at once when the binary matches the sources (content hash next to the .so), so a
+    # stale library with an older ABI is never loaded silently
+    from . import build as _build
+    _build.build()
     lib = C.CDLL(LIB_PATH)
     _declare(lib)
     _lib = lib
