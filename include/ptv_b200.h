@@ -126,6 +126,12 @@ int ptv_knn_stats(const ptv_hash* h, int64_t* used_stream, int64_t* tiles_failed
  * neighbour beyond the histogram range, [2] crossing bin larger than the short list, [3] exact
  * verification failed. */
 int ptv_knn_fail_reasons(const ptv_hash* h, int64_t reasons[4]);
+/* With tuning "stats" = 1: work done by the streaming kernel in the last call -- [0] voxel-candidate pairs
+ * of the histogram passes, [1] pairs of the classification passes (float32 pre-test), [2] exact float64
+ * keys evaluated, [3] crossing-bin list entries, [4] pore voxels finished, [5] rounds (warp passes),
+ * [6] histogram points, [7] retries.  The reference has no counterpart (its search is
+ * interpolator.py:139, one cKDTree.query). */
+int ptv_knn_work_stats(const ptv_hash* h, int64_t work[8]);
 /* With tuning "stats" = 1, after a PTV_METHOD_LINEAR call: [0] voxels finished on the warp-shared candidate
  * set, [1] of those, voxels that re-used the previous voxel's tetrahedron, [2] voxels solved on their own
  * (growing region), [3] candidate sets read from global memory, [4] voxels outside the convex hull,

@@ -23,7 +23,7 @@ _lib = None
 
 EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
-    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_linear_stats", "ptv_knn_points", "ptv_outlier_filter",
+    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_work_stats", "ptv_linear_stats", "ptv_knn_points", "ptv_outlier_filter",
     "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_strain_vorticity", "ptv_poisson_workspace_bytes", "ptv_poisson_lsqr", "ptv_projection_correct",
     "ptv_interpolate_host",
@@ -67,6 +67,8 @@ def _declare(lib):
     lib.ptv_knn_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.ptv_knn_fail_reasons.restype = i32
     lib.ptv_knn_fail_reasons.argtypes = [vp, C.POINTER(i64 * 4)]
+    lib.ptv_knn_work_stats.restype = i32
+    lib.ptv_knn_work_stats.argtypes = [vp, C.POINTER(i64 * 8)]
     lib.ptv_linear_stats.restype = i32
     lib.ptv_linear_stats.argtypes = [vp, C.POINTER(i64 * 8)]
     lib.ptv_mask_gather.restype = i32

@@ -372,6 +372,7 @@ extern "C" int ptv_hash_destroy(ptv_hash* h) {
   cudaFree(h->err_flag);
   cudaFree(h->fail_list);
   cudaFree(h->fail_count);
+  cudaFree(h->fail_flags);
   cudaFree(h->hull_rec);
   cudaFree(h->hull_box);
   cudaFree(h->hull_rec2);

@@ -33,6 +33,8 @@ struct KnnParams {
   // stream kernel -> heap kernel hand-off: tiles the optimistic kernel could not finish
   int* fail_list;        // [capacity]
   int* fail_count;       // [1]
+  unsigned* fail_flags;  // duo kernel: one bit per heap tile, so a tile enters the fail list once
+  int fail_tx, fail_ty, fail_tz;  // shape of the heap kernel's tiles the fail list is expressed in
   const int* tile_list;  // heap kernel: process only these tiles (NULL = all tiles of the grid)
   const int* tile_count;
   unsigned long long* stats;  // optional counters (tiles, failed tiles, candidates, accepted)
@@ -79,8 +81,8 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_tot, int* total)
 }
 
 __device__ __forceinline__ int cell_of(double p, double o, double inv_cell, int n) {
-  const double c = floor((p - o) * inv_cell);  // clamped in double: p may be far outside the grid
-  return (int)fmin(fmax(c, 0.0), (double)(n - 1));
+  // round-down conversion saturates at INT_MIN / INT_MAX (p may be far outside the grid; NaN -> 0)
+  return min(max(__double2int_rd((p - o) * inv_cell), 0), n - 1);
 }
 
 template <typename OutT>
@@ -406,6 +408,8 @@ __device__ __forceinline__ double estimate_radius(const HashGrid& g, const TileG
 // launchers defined next to their kernels
 int launch_knn_heap(KnnParams& p, int T, bool f32, cudaStream_t stream);
 int launch_knn_stream(KnnParams& p, int T, bool f32, cudaStream_t stream);
+int launch_knn_duo(KnnParams& p, bool f32, cudaStream_t stream);
+int launch_knn_sort_lists(KnnParams& p, cudaStream_t stream);
 size_t knn_heap_smem_bytes(int T, int k, int method);
 int launch_delaunay_linear(KnnParams& p, bool f32, cudaStream_t stream);
 int ensure_hull_list(ptv_hash* h, cudaStream_t stream);

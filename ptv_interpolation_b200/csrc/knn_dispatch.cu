@@ -6,6 +6,8 @@
 
 using namespace ptv;
 
+static constexpr int kStatSlots = 24;  // [0] fail count, [1..] stats (see KnnParams::stats)
+
 static int ensure_fail_buffers(ptv_hash* h, int64_t ntiles) {
   if (h->fail_cap < ntiles) {
     cudaFree(h->fail_list);
@@ -14,7 +16,15 @@ static int ensure_fail_buffers(ptv_hash* h, int64_t ntiles) {
     PTV_CUDA(cudaMalloc(&h->fail_list, (size_t)(ntiles + 1024) * sizeof(int)));
     h->fail_cap = ntiles + 1024;
   }
-  if (h->fail_count == nullptr) PTV_CUDA(cudaMalloc(&h->fail_count, 8 * sizeof(unsigned long long)));
+  if (h->fail_count == nullptr) PTV_CUDA(cudaMalloc(&h->fail_count, kStatSlots * sizeof(unsigned long long)));
+  const int64_t words = (ntiles + 31) / 32 + 1;
+  if (h->fail_flags_cap < words) {
+    cudaFree(h->fail_flags);
+    h->fail_flags = nullptr;
+    h->fail_flags_cap = 0;
+    PTV_CUDA(cudaMalloc(&h->fail_flags, (size_t)words * sizeof(unsigned)));
+    h->fail_flags_cap = words;
+  }
   return PTV_OK;
 }
 
@@ -68,7 +78,7 @@ static int run_linear(ptv_hash* h, KnnParams& p, bool f32, cudaStream_t stream) 
   }
   int rc = ensure_fail_buffers(h, 0);
   if (rc != PTV_OK) return rc;
-  PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, 8 * sizeof(unsigned long long), stream));
+  PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, kStatSlots * sizeof(unsigned long long), stream));
   p.stats = tuning().stats != 0 ? h->fail_count + 1 : nullptr;
   if (tuning().hull != 0) {
     rc = ensure_hull_list(h, stream);
@@ -146,6 +156,7 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   p.rscale = tuning().rscale;
   p.err_flag = h->err_flag;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
+  p.fail_flags = nullptr; p.fail_tx = p.fail_ty = p.fail_tz = 1;
   p.qrec = nullptr; p.nq = 0; p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
   p.tiles_x = p.tiles_y = p.tiles_z = 0;
   p.hull_rec = nullptr; p.hull_box = nullptr; p.hull_n = 0;
@@ -154,8 +165,10 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
 
   const size_t smem_max = 227 * 1024;
   const bool f32 = out_dtype == PTV_F32;
+  // the CTA-wide streaming kernel (tuning stream = 1, kept for comparison) cannot output neighbour lists
+  const bool duo = tuning().stream >= 2;
   const bool use_stream = tuning().stream != 0 && (method == PTV_METHOD_IDW || method == PTV_METHOD_SIBSON) &&
-                          k >= 8 && d_knn_idx == nullptr;
+                          k >= 8 && (duo || d_knn_idx == nullptr);
   int T = use_stream ? tuning().stream_tile : tuning().tile;
   if (T != 32 && T != 64 && T != 128) T = 128;
   if (use_stream) {
@@ -176,16 +189,26 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
     if (ntiles > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
     rc = ensure_fail_buffers(h, ntiles);
     if (rc != PTV_OK) return rc;
-    PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, 8 * sizeof(unsigned long long), stream));
+    PTV_CUDA(cudaMemsetAsync(h->fail_count, 0, kStatSlots * sizeof(unsigned long long), stream));
     p.fail_list = h->fail_list;
     p.fail_count = reinterpret_cast<int*>(h->fail_count);
     p.stats = tuning().stats != 0 ? h->fail_count + 1 : nullptr;
-    rc = launch_knn_stream(p, T, f32, stream);
+    if (duo) {
+      PTV_CUDA(cudaMemsetAsync(h->fail_flags, 0, (size_t)((ntiles + 31) / 32 + 1) * sizeof(unsigned), stream));
+      p.fail_flags = h->fail_flags;
+      p.fail_tx = tx; p.fail_ty = ty; p.fail_tz = tz;
+      rc = launch_knn_duo(p, f32, stream);
+    } else {
+      rc = launch_knn_stream(p, T, f32, stream);
+    }
     if (rc != PTV_OK) return rc;
     // exact heap kernel over whatever the optimistic kernel could not finish
     p.tile_list = h->fail_list;
     p.tile_count = reinterpret_cast<const int*>(h->fail_count);
+    p.stats = nullptr;
     rc = launch_knn_heap(p, T, f32, stream);
+    // parity output: canonical order + distances for the rows the streaming kernel selected
+    if (rc == PTV_OK && duo && d_knn_idx != nullptr) rc = launch_knn_sort_lists(p, stream);
   } else {
     rc = launch_knn_heap(p, T, f32, stream);
   }
@@ -215,6 +238,7 @@ static void init_point_params(KnnParams& p, const ptv_hash* h, const ptv_hash* q
   p.rbf_npoly = 4;
   p.err_flag = h->err_flag;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
+  p.fail_flags = nullptr; p.fail_tx = p.fail_ty = p.fail_tz = 1;
   p.qrec = q->rec; p.nq = q->n;
   p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
   p.hull_rec = nullptr; p.hull_box = nullptr; p.hull_n = 0;
@@ -319,6 +343,15 @@ extern "C" int ptv_knn_fail_reasons(const ptv_hash* hc, int64_t reasons[4]) {
   for (int i = 0; i < 4; ++i) reasons[i] = (int64_t)host[2 + i];
   h->last_stage_counts[0] = (int64_t)host[6];
   h->last_stage_counts[1] = (int64_t)host[7];
+  return PTV_OK;
+}
+
+extern "C" int ptv_knn_work_stats(const ptv_hash* h, int64_t work[8]) {
+  if (!h || !work) { set_error("ptv_knn_work_stats: NULL argument"); return PTV_ERR_INVALID; }
+  unsigned long long host[kStatSlots] = {0};
+  if (h->last_used_stream && h->fail_count != nullptr)
+    PTV_CUDA(cudaMemcpy(host, h->fail_count, sizeof(host), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) work[i] = (int64_t)host[9 + i];
   return PTV_OK;
 }
 

@@ -73,10 +73,24 @@ __global__ void __launch_bounds__(T, T == 128 ? 6 : 8) knn_stream_kernel(const K
   int* warp_tot = seg_off + T + 1;
   const PipeBuf pbuf[2] = {{s64, s32, sval}, {s64 + kPipeCap, s32 + kPipeCap, sval + kPipeCap}};
   uint16_t* vlist = reinterpret_cast<uint16_t*>(warp_tot + NW + 1);  // [kVPT*T] compacted active voxels
+  // stats mode only: work counters of this CTA (voxel-candidate pairs of phases A and B/C, exact keys,
+  // crossing-bin list entries), flushed once per CTA
+  unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(vlist + kVPT * T) + 7) & ~(uintptr_t)7);  // [4]
 
   const int t = threadIdx.x;
   const int k = p.k;
   const HashGrid& g = p.g;
+  const bool kStats = p.stats != nullptr;
+  if (kStats && t < 4) wcnt[t] = 0ULL;
+  auto flush_stats = [&](int nvox, int nrounds) {
+    __syncthreads();
+    if (t == 0) {
+      for (int i = 0; i < 4; ++i) atomicAdd(&p.stats[8 + i], wcnt[i]);
+      atomicAdd(&p.stats[12], (unsigned long long)nvox);
+      atomicAdd(&p.stats[13], (unsigned long long)nrounds);
+    }
+  };
   // ---- region of kVPT*T voxels (4x4x4 blocks, block-major) -> compact list of its ACTIVE voxels, so
   //      that every lane of a round owns a pore voxel even where the tile straddles a grain surface
   constexpr int RX = 8, RY = T >= 64 ? 8 : 4, RZ = (T == 128 ? 8 : 4) * (kVPT / 4);
@@ -178,6 +192,7 @@ __global__ void __launch_bounds__(T, T == 128 ? 6 : 8) knn_stream_kernel(const K
     rg = make_region(g, tg, R);
     scan_shell_pipe<T, 0>(g, tg, rg, prev, have_prev, pbuf, seg_start, seg_off, warp_tot, cx, cy, cz,
                           [&](const PipeBuf& pb, int m) {
+      if (kStats && t == 0) wcnt[0] += (unsigned long long)m * round_cnt;
       if (active) {
         const float4* stage32 = pb.stage32;
 #pragma unroll 4
@@ -333,12 +348,14 @@ __global__ void __launch_bounds__(T, T == 128 ? 6 : 8) knn_stream_kernel(const K
   };
   scan_shell_pipe<T, kVal>(g, tg, rg, rg, false, pbuf, seg_start, seg_off, warp_tot, cx, cy, cz,
                            [&](const PipeBuf& pb, int m) {
+    if (kStats && t == 0) wcnt[1] += (unsigned long long)m * round_cnt;
     if (active) {
       const float4* stage32 = pb.stage32;
       const ParticleRec* stage64 = pb.stage64;
       const ValT* stage_val = reinterpret_cast<const ValT*>(pb.stage_val);
       unsigned long long m0 = prefilter64(stage32, 0, hi32);
       unsigned long long m1 = m > 64 ? prefilter64(stage32, 64, hi32) : 0ULL;
+      if (kStats) atomicAdd(&wcnt[2], (unsigned long long)(__popcll(m0) + __popcll(m1)));
       // each thread walks only ITS accepted candidates (dense per lane instead of "any lane")
       while ((m0 | m1) != 0ULL) {
         int j;
@@ -372,6 +389,7 @@ __global__ void __launch_bounds__(T, T == 128 ? 6 : 8) knn_stream_kernel(const K
     }
   });
   const int need = k - n_in;
+  if (kStats && active) atomicAdd(&wcnt[3], (unsigned long long)n_l);
   const bool bad = active && (overflow || need < 0 || need > n_l);
   if (__syncthreads_or(bad ? 1 : 0)) {
     push_fail(4);
@@ -431,6 +449,7 @@ __global__ void __launch_bounds__(T, T == 128 ? 6 : 8) knn_stream_kernel(const K
     const float lo32 = (float)((e_lo + 16.0 * sqrt(e_lo) * ec + 64.0 * ec * ec) * (1.0 + 1e-5));
     scan_shell_pipe<T, kVal>(g, tg, rg, rg, false, pbuf, seg_start, seg_off, warp_tot, cx, cy, cz,
                              [&](const PipeBuf& pb, int m) {
+      if (kStats && t == 0) wcnt[1] += (unsigned long long)m * round_cnt;
       if (active) {
         const float4* stage32 = pb.stage32;
         const ParticleRec* stage64 = pb.stage64;
@@ -465,13 +484,15 @@ __global__ void __launch_bounds__(T, T == 128 ? 6 : 8) knn_stream_kernel(const K
   }
   __syncthreads();  // shared memory is reused by the next round
   }  // rounds
+  if (kStats) flush_stats(nact, rounds);
 }
 
 static size_t stream_smem_bytes(int T, bool f32) {
   const int NW = T / 32;
   size_t b = (size_t)kListCap * T * 12 +
              (size_t)2 * kPipeCap * (sizeof(ParticleRec) + sizeof(float4) + (f32 ? sizeof(float4) : sizeof(Value4))) +
-             (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 2 + NW) * sizeof(int) + (size_t)kVPT * T * sizeof(uint16_t);
+             (size_t)6 * NW * sizeof(double) + (size_t)(2 * T + 2 + NW) * sizeof(int) + (size_t)kVPT * T * sizeof(uint16_t) +
+             4 * sizeof(unsigned long long) + 8;
   return (b + 15) & ~(size_t)15;
 }
 

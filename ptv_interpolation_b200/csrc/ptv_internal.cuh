@@ -41,7 +41,8 @@ struct Tuning {
   double ppc = 0.5;  // target particles per cell (finer cells -> tighter scan regions)
   int r0 = 1;        // rings merged into the first staging batch
   int tile = 128;    // threads (= voxels) per tile, heap kernel
-  int stream = 1;    // 1 = streaming kernel for idw/sibson with k >= 8 (heap kernel as fallback)
+  int stream = 2;    // idw/sibson with k >= 8: 2 = warp-private streaming kernel (knn_duo.cu), 1 = the CTA-wide one
+                     // (knn_stream.cu), 0 = heap kernel only; the heap kernel is always the exact fallback
   int stream_tile = 128;
   int stats = 0;     // 1 = count streamed tiles
   int linear_k = 64;   // method='linear': the first candidate radius is the one expected to hold this many particles (2.5 spacings)
@@ -77,6 +78,8 @@ struct ptv_hash {
   int* err_host = nullptr;        // pinned
   int* fail_list = nullptr;       // tiles handed from the streaming to the heap kernel
   int64_t fail_cap = 0;
+  unsigned* fail_flags = nullptr;  // one bit per heap tile (de-duplicates the fail list)
+  int64_t fail_flags_cap = 0;
   unsigned long long* fail_count = nullptr;  // [0] low 32 bits: fail count; [1]: streamed tiles (stats)
   // method='linear': hull-candidate records and the dominance tables they come from (built on demand)
   ptv::ParticleRec* hull_rec = nullptr;   // stage 1: particles of undominated cells

@@ -220,8 +220,13 @@ class PTVEngine:
         _cabi.check(self.lib.ptv_knn_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         r = (C.c_int64 * 4)()
         _cabi.check(self.lib.ptv_knn_fail_reasons(self._h, C.byref(r)))
+        w = (C.c_int64 * 8)()
+        _cabi.check(self.lib.ptv_knn_work_stats(self._h, C.byref(w)))
+        keys = ("pairs_histogram", "pairs_classify", "exact_keys", "list_entries", "voxels", "rounds",
+                "histogram_points", "retries")
         return {"used_stream": bool(a.value), "tiles_failed": b.value, "tiles_streamed": c.value,
-                "fail_reasons": {"no_estimate": r[0], "beyond_range": r[1], "bin_overflow": r[2], "verify": r[3]}}
+                "fail_reasons": {"no_estimate": r[0], "beyond_range": r[1], "bin_overflow": r[2], "verify": r[3]},
+                "work": dict(zip(keys, (int(v) for v in w)))}
 
     def linear_stats(self):
         """Diagnostics of the last method='linear' call (needs set_tuning(stats=1))."""
