@@ -239,7 +239,7 @@ __device__ __noinline__ int duo_next_chunk(const HashGrid* gs, unsigned char* wb
           if (with_exact) {
             int4* dst = reinterpret_cast<int4*>(L::s64(wb) + j);
             dst[0] = a;
-            dst[1] = c;
+            dst[1] = make_int4(c.x, c.y, c.z, spos);  // pad word: the record's cell-sorted position
             L::sval(wb)[j] = DuoVal<OutT>::load(g, spos);
           }
         } else if (j < mpad) {
@@ -347,6 +347,26 @@ __device__ __forceinline__ double exact_from_rows(const HashGrid& g, double qx, 
   const double ex = qx - pr[0], ey = qy - pr[1], ez = qz - pr[2];
   return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
 }
+// The same key from the cell-sorted record (the lists hold sorted positions: those lines were just staged,
+// so the gather hits L2 / L1 instead of the original-order arrays); also returns the particle row.
+__device__ __forceinline__ double exact_from_rec(const HashGrid& g, double qx, double qy, double qz, int spos, int& row) {
+  const int4* src = reinterpret_cast<const int4*>(g.rec + spos);
+  const int4 a = __ldg(src);
+  const int4 c = __ldg(src + 1);
+  row = c.z;
+  const double ex = qx - __hiloint2double(a.y, a.x), ey = qy - __hiloint2double(a.w, a.z);
+  const double ez = qz - __hiloint2double(c.y, c.x);
+  return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+}
+__device__ __forceinline__ Value4 sorted_value(const HashGrid& g, int spos, int f32vals) {
+  if (f32vals) {
+    const float4 v = __ldg(g.vals_s32 + spos);
+    Value4 r;
+    r.u = (double)v.x; r.v = (double)v.y; r.w = (double)v.z; r.pad = 0.0;
+    return r;
+  }
+  return g.vals_s64[spos];
+}
 
 // The `nd` smallest (d2, row) entries of one voxel's crossing-bin list, moved to the front of the list.
 // Keys are float32 offsets from E_lo (monotone in the exact key); entries whose offsets are equal across
@@ -382,8 +402,8 @@ __device__ __noinline__ void duo_select(const HashGrid* gs, float* lk, int* li, 
     double bk = 0.0;
     for (int j = i; j < nl; ++j) {
       if (lk[j * 32] != cut) continue;
-      const int ij = li[j * 32];
-      const double kj = exact_from_rows(*gs, qx, qy, qz, ij);
+      int ij;
+      const double kj = exact_from_rec(*gs, qx, qy, qz, li[j * 32], ij);
       if (best < 0 || key_greater(bk, bi, kj, ij)) { best = j; bk = kj; bi = ij; }
     }
     if (best != i) {
@@ -402,15 +422,16 @@ struct DuoAcc {
 };
 // IDW: weights of the first nd list entries -> (sum w, sum w u, sum w v, sum w w).
 __device__ __noinline__ DuoAcc duo_list_idw(const HashGrid* gs, float* lk, int* li, int nl, int nd, double qx, double qy,
-                                            double qz, double power, int64_t* dbg) {
+                                            double qz, double power, int f32vals, int64_t* dbg) {
   DuoAcc r = {0.0, 0.0, 0.0, 0.0};
   duo_select(gs, lk, li, nl, nd, qx, qy, qz);
   for (int i = 0; i < nd; ++i) {
-    const int row = li[i * 32];
+    const int spos = li[i * 32];
+    int row;
+    const double d2 = exact_from_rec(*gs, qx, qy, qz, spos, row);
     if (dbg != nullptr) dbg[i] = row;
-    const double d2 = exact_from_rows(*gs, qx, qy, qz, row);
     const double wgt = power == 2.0 ? 1.0 / (d2 + 1e-10) : duo_pow_weight(d2, power);
-    const Value4 val = gs->vals[row];
+    const Value4 val = sorted_value(*gs, spos, f32vals);
     r.a += wgt;
     r.b += wgt * val.u;
     r.c += wgt * val.v;
@@ -424,9 +445,9 @@ __device__ __noinline__ DuoAcc duo_list_moments(const HashGrid* gs, float* lk, i
   DuoAcc r = {0.0, 0.0, 0.0, 0.0};
   duo_select(gs, lk, li, nl, nd, qx, qy, qz);
   for (int i = 0; i < nd; ++i) {
-    const int row = li[i * 32];
+    int row;
+    const double dd = sqrt(exact_from_rec(*gs, qx, qy, qz, li[i * 32], row)) - dshift;
     if (dbg != nullptr) dbg[i] = row;
-    const double dd = sqrt(exact_from_rows(*gs, qx, qy, qz, row)) - dshift;
     r.a += dd;
     r.b += dd * dd;
   }
@@ -434,13 +455,14 @@ __device__ __noinline__ DuoAcc duo_list_moments(const HashGrid* gs, float* lk, i
 }
 // sibson, second pass: w = (1/(d+eps)) * exp(-d / (std(d) + eps))  (interpolator.py:102-122)
 __device__ __noinline__ DuoAcc duo_list_sibson(const HashGrid* gs, const int* li, int nd, double qx, double qy,
-                                               double qz, double inv_s) {
+                                               double qz, double inv_s, int f32vals) {
   DuoAcc r = {0.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < nd; ++i) {
-    const int row = li[i * 32];
-    const double d = sqrt(exact_from_rows(*gs, qx, qy, qz, row));
+    const int spos = li[i * 32];
+    int row;
+    const double d = sqrt(exact_from_rec(*gs, qx, qy, qz, spos, row));
     const double wgt = (1.0 / (d + 1e-10)) * exp(-d * inv_s);
-    const Value4 val = gs->vals[row];
+    const Value4 val = sorted_value(*gs, spos, f32vals);
     r.a += wgt;
     r.b += wgt * val.u;
     r.c += wgt * val.v;
@@ -837,51 +859,68 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
         // float32 output: the weights of one group of candidates are summed in float32 (<= 32 terms), the
         // groups in float64
         float gw[2] = {0.0f, 0.0f}, gu[2] = {0.0f, 0.0f}, gv[2] = {0.0f, 0.0f}, gq[2] = {0.0f, 0.0f};
-        // each lane walks only ITS accepted candidates, one of each voxel per trip
+        // each lane walks only ITS accepted candidates, one of each voxel per trip; straight-line code so
+        // that the two independent evaluations overlap (a voxel that has run out re-reads slot `base` with
+        // every effect masked)
         while ((mk[0] | mk[1]) != 0u) {
+          bool on[2], in[2];
+          int j[2], sp[2];
+          double d2[2];
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            if (mk[v] != 0u) {
-              const int j = base + __ffs((int)mk[v]) - 1;
-              mk[v] &= mk[v] - 1u;
-              const double2 xy = *reinterpret_cast<const double2*>(&s64[j].x);
-              const double zz = s64[j].z;
-              const double ex = qx[v] - xy.x, ey = qy[v] - xy.y, ez = qz[v] - zz;
-              const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-              if (d2 < e_lo[v]) {
-                if (dbg && n_in[v] < k) p.knn_idx[vox[v] * k + n_in[v]] = s64[j].idx;
-                ++n_in[v];
-                if (kMode == kModeSibson) {
-                  const double dd = sqrt(d2) - dshift[v];
-                  wsum[v] += dd;  // moments first; the weights need the std of all k distances
-                  su[v] += dd * dd;
-                } else if (kF32) {
-                  float wgt;
-                  if (p2) {  // the weight only needs float32 accuracy: MUFU.RCP, 1 ulp
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(wgt) : "f"((float)d2 + 1e-10f));
-                  } else {
-                    wgt = (float)duo_pow_weight(d2, p.power);
-                  }
-                  const float4 val = *reinterpret_cast<const float4*>(&sval[j]);
-                  gw[v] += wgt;
-                  gu[v] = fmaf(wgt, val.x, gu[v]);
-                  gv[v] = fmaf(wgt, val.y, gv[v]);
-                  gq[v] = fmaf(wgt, val.z, gq[v]);
-                } else {
-                  const double wgt = p2 ? 1.0 / (d2 + 1e-10) : duo_pow_weight(d2, p.power);
-                  const ValT val = sval[j];
-                  wsum[v] += wgt;
-                  su[v] += wgt * DuoVal<OutT>::u(val);
-                  sv[v] += wgt * DuoVal<OutT>::v(val);
-                  sw[v] += wgt * DuoVal<OutT>::w(val);
-                }
-              } else if (d2 < e_hi[v]) {
-                if (n_l[v] < kDList) {
-                  lkey[(v * kDList + n_l[v]) * 32] = (float)(d2 - e_lo[v]);
-                  lidx[(v * kDList + n_l[v]) * 32] = s64[j].idx;
-                }
-                ++n_l[v];  // > kDList: overflow
+            on[v] = mk[v] != 0u;
+            j[v] = base + (on[v] ? __ffs((int)mk[v]) - 1 : 0);
+            mk[v] &= mk[v] - 1u;  // 0 stays 0
+          }
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const double2 xy = *reinterpret_cast<const double2*>(&s64[j[v]].x);
+            const int4 zi = *reinterpret_cast<const int4*>(&s64[j[v]].z);  // z, particle row, sorted position
+            sp[v] = zi.w;
+            const double ex = qx[v] - xy.x, ey = qy[v] - xy.y, ez = qz[v] - __hiloint2double(zi.y, zi.x);
+            d2[v] = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+            in[v] = on[v] && d2[v] < e_lo[v];
+            if (dbg && in[v] && n_in[v] < k) p.knn_idx[vox[v] * k + n_in[v]] = zi.z;
+            n_in[v] += in[v] ? 1 : 0;
+          }
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            if (kMode == kModeSibson) {
+              const double dd = in[v] ? sqrt(d2[v]) - dshift[v] : 0.0;
+              wsum[v] += dd;  // moments first; the weights need the std of all k distances
+              su[v] += dd * dd;
+            } else if (kF32) {
+              float wgt;
+              if (p2) {  // the weight only needs float32 accuracy: MUFU.RCP, 1 ulp
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(wgt) : "f"((float)d2[v] + 1e-10f));
+              } else {
+                wgt = in[v] ? (float)duo_pow_weight(d2[v], p.power) : 0.0f;
               }
+              wgt = in[v] ? wgt : 0.0f;
+              const float4 val = *reinterpret_cast<const float4*>(&sval[j[v]]);
+              gw[v] += wgt;
+              gu[v] = fmaf(wgt, val.x, gu[v]);
+              gv[v] = fmaf(wgt, val.y, gv[v]);
+              gq[v] = fmaf(wgt, val.z, gq[v]);
+            } else {
+              double wgt = 0.0;
+              if (in[v]) wgt = p2 ? 1.0 / (d2[v] + 1e-10) : duo_pow_weight(d2[v], p.power);
+              const ValT val = sval[j[v]];
+              wsum[v] += wgt;
+              su[v] += wgt * DuoVal<OutT>::u(val);
+              sv[v] += wgt * DuoVal<OutT>::v(val);
+              sw[v] += wgt * DuoVal<OutT>::w(val);
+            }
+          }
+          // crossing-bin candidates -> the voxel's list (float32 offset from E_lo, sorted position)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            if (on[v] && !in[v] && d2[v] < e_hi[v]) {
+              if (n_l[v] < kDList) {
+                lkey[(v * kDList + n_l[v]) * 32] = (float)(d2[v] - e_lo[v]);
+                lidx[(v * kDList + n_l[v]) * 32] = sp[v];
+              }
+              ++n_l[v];  // > kDList: overflow
             }
           }
         }
@@ -920,7 +959,7 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
         su[v] += a.b;
       } else {
         const DuoAcc a = duo_list_idw(gs, lkey + v * kDList * 32, lidx + v * kDList * 32, n_l[v], need[v], qx[v], qy[v],
-                                      qz[v], p.power, dptr);
+                                      qz[v], p.power, kF32 ? 1 : 0, dptr);
         wsum[v] += a.a;
         su[v] += a.b;
         sv[v] += a.c;
@@ -942,7 +981,7 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
         thr_lo[v] = ok[v] ? lim32(e_lo[v]) - q2 : -INFINITY;
         wsum[v] = su[v] = sv[v] = sw[v] = 0.0;
         if (ok[v]) {
-          const DuoAcc a = duo_list_sibson(gs, lidx + v * kDList * 32, need[v], qx[v], qy[v], qz[v], inv_s[v]);
+          const DuoAcc a = duo_list_sibson(gs, lidx + v * kDList * 32, need[v], qx[v], qy[v], qz[v], inv_s[v], kF32 ? 1 : 0);
           wsum[v] = a.a;
           su[v] = a.b;
           sv[v] = a.c;

@@ -16,7 +16,7 @@ import math
 import torch
 
 __all__ = ["hex6_sphere_pack_mask", "fcc_sphere_pack_mask", "cylinder_array_mask", "sample_pore_particles",
-           "sphere_pack_flow", "cylinder_flow", "make_config"]
+           "sphere_pack_flow", "cylinder_flow", "wall_particles", "make_config"]
 
 
 def _axes(n, device):
@@ -134,13 +134,37 @@ def cylinder_flow(points, pitch=64.0, radius_frac=0.25, U0=1.0):
     return torch.stack([u, v, w], -1).to(torch.float32).to(torch.float64)
 
 
+def wall_particles(mask, sampling_step=50, thickness=2):
+    """Zero-velocity ghost particles on the grain surfaces, as interpolate_porous_glass.py:68-71 asks for
+    (--boundary-particles, sampling 50, thickness 2) and main.py:164-178 builds them: solid voxels within
+    ``thickness`` 6-connected dilation steps of the fluid (interpolator.py:256-262), C order, every
+    ``sampling_step``-th (:271-274), at their voxel coordinates (bounds (0,n): physical = index, :280-282).
+    Input synthesis in torch -- the product path is extract_boundary_particles."""
+    fluid = mask.clone()
+    for _ in range(int(thickness)):
+        d = fluid.clone()
+        d[1:] |= fluid[:-1]
+        d[:-1] |= fluid[1:]
+        d[:, 1:] |= fluid[:, :-1]
+        d[:, :-1] |= fluid[:, 1:]
+        d[:, :, 1:] |= fluid[:, :, :-1]
+        d[:, :, :-1] |= fluid[:, :, 1:]
+        fluid = d
+    lin = torch.nonzero((fluid & ~mask).reshape(-1)).squeeze(1)[::int(sampling_step)]
+    nz, ny, nx = mask.shape
+    z, rem = lin // (ny * nx), lin % (ny * nx)
+    y, x = rem // nx, rem % nx
+    return torch.stack([x, y, z], -1).to(torch.float64)
+
+
 def make_config(name, device="cpu", seed=None):
     """Inputs of one BASELINE.json config: dict(mask, points, values, n, method, k, ...).
-    C1 hex6 128^3/100k, C2 cylinders 256^3/1M, C3 fcc 512^3/5M, C4 fcc 1024^3/10M."""
+    C1 hex6 128^3/100k, C2 cylinders 256^3/1M, C3 fcc 512^3/5M + wall particles (every 50th boundary voxel,
+    thickness 2: the porous-glass launcher's settings), C4 fcc 1024^3/10M."""
     spec = {
         "c1": dict(n=128, npts=100_000, geom="hex6", method="idw", k=50, seed=1),
         "c2": dict(n=256, npts=1_000_000, geom="cyl", method="idw", k=50, seed=2),
-        "c3": dict(n=512, npts=5_000_000, geom="fcc", method="sibson", k=50, seed=3),
+        "c3": dict(n=512, npts=5_000_000, geom="fcc", method="sibson", k=50, seed=3, walls=(50, 2)),
         "c4": dict(n=1024, npts=10_000_000, geom="fcc", method="idw", k=50, seed=4),
     }[name]
     n = spec["n"]
@@ -153,6 +177,10 @@ def make_config(name, device="cpu", seed=None):
         mask = fcc_sphere_pack_mask(n, device=device)
     pts = sample_pore_particles(mask, spec["npts"], seed=sd)
     vals = cylinder_flow(pts) if spec["geom"] == "cyl" else sphere_pack_flow(pts, n)
+    if spec.get("walls"):
+        wp = wall_particles(mask, *spec["walls"])
+        pts = torch.cat([pts, wp], 0)
+        vals = torch.cat([vals, torch.zeros_like(wp)], 0)
     out = dict(spec)
     out.update(mask=mask, points=pts, values=vals, bounds=((0, n), (0, n), (0, n)))
     return out

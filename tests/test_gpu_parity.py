@@ -194,6 +194,9 @@ def test_sphere_pack_vs_oracle(masked, method, k):
     kw = dict(method=method, idw_neighbors=k, sibson_neighbors=k)
     U, V, W, kd, ki = gi.interpolate_field(_df(pts, vals), grid, mask=mask if masked else None,
                                            return_knn=True, **kw)
+    from ptv_interpolation_b200.engine import default_engine
+    # k >= 8: the neighbour lists come from the PRODUCTION streaming kernel (knn_duo_kernel + canonical sort)
+    assert default_engine().knn_stats()["used_stream"] == (k >= 8)
     og, _ = rp.create_grid(b, n)
     Ur, Vr, Wr, d, i = rp.interpolate_field(pts, vals, og, return_knn=True, **kw)
     ref = np.stack([Ur, Vr, Wr])
@@ -220,19 +223,22 @@ def test_tuning_does_not_change_neighbours(case_a, tune):
     assert np.array_equal(ki, g["knn_i_k50"]) and np.array_equal(kd, g["knn_d_k50"])
 
 
-def _stream_vs_heap(df, grid, mask=None, **kw):
-    """float64 outputs of the streaming kernel and of the exact heap kernel: the neighbour SETS are
+STREAM_DEFAULT = 2  # Tuning::stream: 2 = warp-private streaming kernel (production), 1 = CTA-wide one
+
+
+def _stream_vs_heap(df, grid, mask=None, stream=STREAM_DEFAULT, **kw):
+    """float64 outputs of a streaming kernel and of the exact heap kernel: the neighbour SETS are
     identical iff the weighted means agree to summation-order rounding."""
     from ptv_interpolation_b200.engine import default_engine
     try:
-        set_tuning(stream=1, stats=1)
+        set_tuning(stream=stream, stats=1)
         a = np.stack(gi.interpolate_field(df, grid, mask=mask, out_dtype=np.float64, **kw))
         st = default_engine().knn_stats()
         set_tuning(stream=0)
         b = np.stack(gi.interpolate_field(df, grid, mask=mask, out_dtype=np.float64, **kw))
         assert not default_engine().knn_stats()["used_stream"]
     finally:
-        set_tuning(stream=1, stats=0)
+        set_tuning(stream=STREAM_DEFAULT, stats=0)
     assert st["used_stream"]
     scale = np.abs(b).max()
     assert np.abs(a - b).max() <= 1e-11 * scale, float(np.abs(a - b).max() / scale)
@@ -243,16 +249,18 @@ def _stream_vs_heap(df, grid, mask=None, **kw):
                                   dict(ppc=0.4), dict(ppc=5.0)])
 @pytest.mark.parametrize("kw", [dict(method="idw"), dict(method="idw", idw_neighbors=9, idw_power=3.0),
                                 dict(method="sibson"), dict(method="sibson", sibson_neighbors=50)])
-def test_stream_kernel_matches_heap_kernel(case_a, tune, kw):
+@pytest.mark.parametrize("stream", [2, 1])
+def test_stream_kernel_matches_heap_kernel(case_a, tune, kw, stream):
     g, grid, df = case_a
     try:
         set_tuning(**tune)
-        _stream_vs_heap(df, grid, **kw)
+        _stream_vs_heap(df, grid, stream=stream, **kw)
     finally:
         set_tuning(stream_tile=128, r0=1, ppc=0.5)
 
 
-def test_stream_kernel_sphere_pack_and_fallback_paths():
+@pytest.mark.parametrize("stream", [2, 1])
+def test_stream_kernel_sphere_pack_and_fallback_paths(stream):
     n = 48
     mask = synthetic.hex6_sphere_pack_mask(n)
     pts = synthetic.sample_pore_particles(mask, 12000, seed=5)
@@ -260,10 +268,11 @@ def test_stream_kernel_sphere_pack_and_fallback_paths():
     pts, vals, mask = pts.numpy(), vals.numpy(), mask.numpy()
     grid, _ = gi.create_grid(((0, n), (0, n), (0, n)), n)
     # pore voxels only: nearly every tile stays on the streaming kernel
-    a, st = _stream_vs_heap(_df(pts, vals), grid, mask=mask, method="idw")
-    assert st["tiles_streamed"] > 0 and st["tiles_failed"] < 0.2 * (st["tiles_streamed"] + st["tiles_failed"])
+    a, st = _stream_vs_heap(_df(pts, vals), grid, mask=mask, stream=stream, method="idw")
+    # nearly every pore voxel is finished by the streaming kernel itself
+    assert st["tiles_streamed"] > 0 and st["work"]["voxels"] > 0.8 * int(mask.sum())
     # all voxels: tiles deep inside the grains have no local density estimate -> heap fallback
-    b, st2 = _stream_vs_heap(_df(pts, vals), grid, method="idw")
+    b, st2 = _stream_vs_heap(_df(pts, vals), grid, stream=stream, method="idw")
     assert st2["tiles_failed"] > 0
     assert np.abs(a[:, mask] - b[:, mask]).max() <= 1e-11 * np.abs(b).max()
     # lattice + exact duplicates + a pile of coincident points: tie groups overflow the short list
@@ -273,7 +282,7 @@ def test_stream_kernel_sphere_pack_and_fallback_paths():
                             rng.uniform(0, 9, size=(500, 3)).astype(np.float32).astype(np.float64)], 0)
     cv = rng.normal(size=(len(cloud), 3))
     g2, _ = gi.create_grid(((0, 10), (0, 10), (0, 10)), 10)
-    c, st3 = _stream_vs_heap(_df(cloud, cv), g2, method="idw", idw_neighbors=30)
+    c, st3 = _stream_vs_heap(_df(cloud, cv), g2, stream=stream, method="idw", idw_neighbors=30)
     assert st3["tiles_failed"] > 0
     og, _ = rp.create_grid(((0, 10), (0, 10), (0, 10)), 10)
     d, i, _ = rp.knn_bruteforce(cloud, rp.flat_coords(og), 30)
@@ -506,6 +515,72 @@ def test_c3_size_sibson_sampled_voxels_vs_oracle():
     ref = rp.sibson_from_knn(d, i, vals).T
     got = out.reshape(3, -1)[:, sel].cpu().numpy()
     _assert_vel(got[:, None, None, :], ref[:, None, None, :], vals)
+
+
+def test_c4_headline_config_sampled_voxels_vs_oracle():
+    """Config 4 -- the benchmarked workload (1024^3 FCC pack, 10M vectors, IDW k=50): 24k random pore voxels
+    of the full-grid float32 result against the oracle (cKDTree over all 10M particles, canonical order,
+    interpolator.py:126-155), the share of voxels the streaming kernel hands to the exact heap kernel, and
+    the z-slab launch the multi-GPU path uses against the whole-grid launch."""
+    dev = torch.device("cuda", 0)
+    cfg, n, ax = _full_size_case("c4", dev)
+    eng = PTVEngine(dev)
+    mask = cfg["mask"].view(torch.uint8)
+    eng.build(cfg["points"], cfg["values"])
+    try:
+        set_tuning(stats=1)
+        out = eng.interpolate(ax, ax, ax, mask=mask, method="idw", k=50)
+        st = eng.knn_stats()
+    finally:
+        set_tuning(stats=0)
+    pore = int(cfg["mask"].sum())
+    assert st["used_stream"]
+    # the fail list holds 8x4x4 heap tiles: fewer than 0.1 % of the volume is redone by the exact kernel
+    assert st["tiles_failed"] * 128 < 1e-3 * n ** 3, st
+    assert st["work"]["voxels"] > 0.999 * pore
+    assert torch.all(out[:, ~cfg["mask"]] == 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    lin = torch.nonzero(cfg["mask"].reshape(-1)).squeeze(1)
+    sel = lin[torch.randint(0, lin.numel(), (24000,), generator=g, device=dev)]
+    zz, rem = sel // (n * n), sel % (n * n)
+    yy, xx = rem // n, rem % n
+    q = torch.stack([xx, yy, zz], -1).to(torch.float64).cpu().numpy()
+    pts, vals = cfg["points"].cpu().numpy(), cfg["values"].cpu().numpy()
+    d, i, _ = rp.knn_canonical(pts, q, 50, workers=-1)
+    ref = rp.idw_from_knn(d, i, vals).T
+    got = out.reshape(3, -1)[:, sel].cpu().numpy()
+    _assert_vel(got[:, None, None, :], ref[:, None, None, :], vals)
+    # a z-slab launch (what rank r of N computes) is bit-identical to the same planes of the whole grid
+    z0, z1 = 384, 512
+    part = eng.interpolate(ax, ax, ax[z0:z1], mask=mask[z0:z1], method="idw", k=50)
+    assert torch.equal(part, out[:, z0:z1])
+
+
+def test_production_kernel_neighbour_rows_bitexact_c1_scale():
+    """Neighbour rows and distances of the PRODUCTION streaming kernel (not the heap kernel) at config-1
+    density: 64^3 hex pack, 12.5k vectors, k = 50 and sibson k = 30, against the canonical cKDTree lists."""
+    from ptv_interpolation_b200.engine import default_engine
+    n = 64
+    mask = synthetic.hex6_sphere_pack_mask(n)
+    pts = synthetic.sample_pore_particles(mask, 12500, seed=21)
+    vals = synthetic.sphere_pack_flow(pts, n)
+    pts, vals, mask = pts.numpy(), vals.numpy(), mask.numpy()
+    b = ((0, n), (0, n), (0, n))
+    grid, _ = gi.create_grid(b, n)
+    og, _ = rp.create_grid(b, n)
+    sel = mask.ravel()
+    for kw in (dict(method="idw", idw_neighbors=50), dict(method="sibson", sibson_neighbors=30)):
+        try:
+            set_tuning(stats=1)
+            U, V, W, kd, ki = gi.interpolate_field(_df(pts, vals), grid, mask=mask, return_knn=True, **kw)
+            st = default_engine().knn_stats()
+        finally:
+            set_tuning(stats=0)
+        assert st["used_stream"] and st["work"]["voxels"] > 0.9 * int(sel.sum())
+        Ur, Vr, Wr, d, i = rp.interpolate_field(pts, vals, og, return_knn=True, **kw)
+        assert np.array_equal(ki[sel], i[sel]) and np.array_equal(kd[sel], d[sel])
+        _assert_vel(np.stack([U, V, W]), np.stack(rp.apply_mask_zero(Ur, Vr, Wr, mask)), vals)
 
 
 # ------------------------------------------------------------------ N1: outlier filter + point queries
