@@ -422,9 +422,25 @@ struct DuoAcc {
 };
 // IDW: weights of the first nd list entries -> (sum w, sum w u, sum w v, sum w w).
 __device__ __noinline__ DuoAcc duo_list_idw(const HashGrid* gs, float* lk, int* li, int nl, int nd, double qx, double qy,
-                                            double qz, double power, int f32vals, int64_t* dbg) {
+                                            double qz, double power, double e_lo, int f32vals, int64_t* dbg) {
   DuoAcc r = {0.0, 0.0, 0.0, 0.0};
   duo_select(gs, lk, li, nl, nd, qx, qy, qz);
+  if (f32vals && dbg == nullptr && power == 2.0) {
+    // float32 output: E_lo + offset is the key to ~3e-9 relative, far inside what the float32 weight keeps,
+    // so only the value is gathered (one 16-byte line the stager touched a moment ago)
+#pragma unroll 2
+    for (int i = 0; i < nd; ++i) {
+      const float4 val = __ldg(gs->vals_s32 + li[i * 32]);
+      float wf;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(wf) : "f"((float)(e_lo + (double)lk[i * 32]) + 1e-10f));
+      const double wgt = (double)wf;
+      r.a += wgt;
+      r.b += wgt * (double)val.x;
+      r.c += wgt * (double)val.y;
+      r.d += wgt * (double)val.z;
+    }
+    return r;
+  }
   for (int i = 0; i < nd; ++i) {
     const int spos = li[i * 32];
     int row;
@@ -959,7 +975,7 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
         su[v] += a.b;
       } else {
         const DuoAcc a = duo_list_idw(gs, lkey + v * kDList * 32, lidx + v * kDList * 32, n_l[v], need[v], qx[v], qy[v],
-                                      qz[v], p.power, kF32 ? 1 : 0, dptr);
+                                      qz[v], p.power, e_lo[v], kF32 ? 1 : 0, dptr);
         wsum[v] += a.a;
         su[v] += a.b;
         sv[v] += a.c;
