@@ -140,10 +140,15 @@ def sibson_from_knn(distances, indices, values):
     return out
 
 
+def _rbf_worker(interp, chunk):
+    """interpolator.py:62-63"""
+    return interp(chunk)
+
+
 def interpolate_field(points, values, grid_tuple, method="idw", rbf_neighbors=20,
                       rbf_kernel="thin_plate_spline", smoothing=0.0, idw_power=2.0,
                       idw_neighbors=50, sibson_neighbors=30, workers=1, chunk_voxels=1 << 18,
-                      canonical=True, return_knn=False):
+                      canonical=True, return_knn=False, n_jobs=1):
     """interpolator.py:65-203 for methods idw / sibson / rbf / nearest, driven in voxel
     chunks so large grids fit in RAM (per-voxel results do not depend on the chunking:
     the tree always holds every particle).  ``points``/``values`` are the (Np,3) float64
@@ -182,8 +187,17 @@ def interpolate_field(points, values, grid_tuple, method="idw", rbf_neighbors=20
         from scipy.interpolate import RBFInterpolator
         interp = RBFInterpolator(points, values, neighbors=rbf_neighbors, kernel=rbf_kernel,
                                  smoothing=smoothing)
-        for s in range(0, nq, 10000):
-            out[s:s + 10000] = interp(fc[s:s + 10000])
+        if n_jobs > 1:
+            # interpolator.py:173-182 (the test_parallel.py mode): the voxels are split into n_jobs
+            # contiguous chunks, the interpolator is pickled to every worker, results are stacked
+            from concurrent.futures import ProcessPoolExecutor
+            chunks = np.array_split(fc, n_jobs)
+            with ProcessPoolExecutor(max_workers=n_jobs) as executor:
+                results = list(executor.map(_rbf_worker, [interp] * n_jobs, chunks))
+            out[:] = np.vstack(results)
+        else:
+            for s in range(0, nq, 10000):
+                out[s:s + 10000] = interp(fc[s:s + 10000])
     elif method == "nearest":
         # interpolator.py:197 griddata(method='nearest') == cKDTree k=1 lookup
         dist, idx, _ = knn_canonical(points, fc, 1, workers=workers)

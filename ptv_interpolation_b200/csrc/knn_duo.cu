@@ -5,7 +5,7 @@
 // thresholds E_lo < E_hi per voxel -> exact classification, never a per-voxel k-best list), but the
 // unit of work is a WARP, not a CTA:
 //
-//   * a CTA owns an 8x8x16 region of voxels and compacts its pore voxels (4x4x4-block-major order);
+//   * a CTA owns an 8x8x32 region of voxels and compacts its pore voxels (4x4x4-block-major order);
 //     warps take chunks of 64 consecutive pore voxels from that list (dynamic), each lane owns two;
 //   * every warp scans the cell list around the bounding box of ITS 64 voxels through its own
 //     4 KB staging buffer -- no block barrier after the compaction, and the scanned volume is that of
@@ -33,7 +33,8 @@ static constexpr int kDList = 16;  // crossing-bin list capacity per voxel
 static constexpr int kDCH = 64;    // records per staged chunk
 static constexpr int kDW = 4;      // warps per CTA
 static constexpr int kDT = kDW * 32;
-static constexpr int kDVPT = 8;    // voxels of the region per thread (region = 8 x 8 x 16)
+static constexpr int kDVPT = 16;   // voxels of the region per thread (region = 8 x 8 x 32)
+static constexpr int kDRZ = 32;    // z-extent of a CTA's region: ~14 chunks for 4 warps keeps the CTA's tail short
 static constexpr int kDMinEstimate = 16;
 static constexpr unsigned kFull = 0xffffffffu;
 static constexpr int kModeIdw = 0, kModeSibson = 2;
@@ -546,10 +547,10 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
     *next_chunk = 0;
   }
 
-  // ---- region of 8 x 8 x 16 voxels (4x4x4 blocks, block-major) -> compact list of its pore voxels.
+  // ---- region of 8 x 8 x 32 voxels (4x4x4 blocks, block-major) -> compact list of its pore voxels.
   //      A thread owns two x-rows of four voxels of one block.
-  constexpr int RX = 8, RY = 8, RZ = 16, NBX = RX / 4, NBY = RY / 4;
-  static_assert(RX * RY * RZ == kDVPT * kDT && kDVPT == 8, "region holds 8 voxels per thread");
+  constexpr int RX = 8, RY = 8, RZ = kDRZ, NBX = RX / 4, NBY = RY / 4;
+  static_assert(RX * RY * RZ == kDVPT * kDT && kDVPT % 4 == 0 && kDVPT <= 32, "region holds kDVPT voxels per thread");
   const int region = blockIdx.x;
   const int rx = region % p.tiles_x;
   const int ry = (region / p.tiles_x) % p.tiles_y;
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
                         ((reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.v) |
                           reinterpret_cast<uintptr_t>(p.w)) & 15) == 0;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < kDVPT / 4; ++r) {
       int ix, iy, iz;
       decode(kDVPT * t + 4 * r, ix, iy, iz);
       if (iy >= p.ny || iz >= p.nz || ix >= p.nx) continue;
@@ -1138,7 +1139,7 @@ template <typename OutT, int kMode, bool kDiag>
 static int launch_duo_t(KnnParams& p, cudaStream_t stream) {
   p.tiles_x = (p.nx + 7) / 8;
   p.tiles_y = (p.ny + 7) / 8;
-  p.tiles_z = (p.nz + 15) / 16;
+  p.tiles_z = (p.nz + kDRZ - 1) / kDRZ;
   const int64_t nreg = (int64_t)p.tiles_x * p.tiles_y * p.tiles_z;
   if (nreg > 2147483647LL) { set_error("ptv_knn_interp: grid too large for one launch"); return PTV_ERR_INVALID; }
   const size_t smem = duo_smem_bytes<OutT>();

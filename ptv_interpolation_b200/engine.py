@@ -150,9 +150,10 @@ class PTVEngine:
     def interpolate_to_host(self, ax_x, ax_y, ax_z, host_out, mask=None, dev_out=None, chunks=None, **kw):
         """interpolate() with the device->host copy of U,V,W overlapped with the search: the slab is
         processed in z-chunks on the current stream while a second stream drains finished chunks into
-        ``host_out`` (a pinned (3,nz,ny,nx) CPU tensor).  Returns the device tensor; the caller must
-        synchronise (``torch.cuda.synchronize()`` or ``self.copy_stream.synchronize()``) before reading
-        ``host_out``."""
+        ``host_out`` (a pinned (3,nz,ny,nx) CPU tensor) -- one copy per chunk and component, each a
+        contiguous block.  Returns (device tensor, completion event): ``host_out`` may be read after
+        ``event.synchronize()``.  A ``dev_out`` given by the caller may be reused for the next frame at
+        once: the main stream waits for the previous drain before the first kernel overwrites it."""
         nx, ny, nz = ax_x.numel(), ax_y.numel(), ax_z.numel()
         if dev_out is None:
             dev_out = torch.empty((3, nz, ny, nx), dtype=host_out.dtype, device=self.device)
@@ -163,6 +164,10 @@ class PTVEngine:
         if not hasattr(self, "copy_stream"):
             self.copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
+        # a reused dev_out must not be overwritten while an earlier drain still reads it
+        main.wait_stream(self.copy_stream)
+        # the drain runs on copy_stream: keep the block out of the caching allocator until it is done
+        dev_out.record_stream(self.copy_stream)
         cuts = [round(i * nz / chunks) for i in range(chunks + 1)]
         for a, b in zip(cuts[:-1], cuts[1:]):
             if b <= a:
@@ -175,7 +180,9 @@ class PTVEngine:
             with torch.cuda.stream(self.copy_stream):
                 for c in range(3):
                     host_out[c, a:b].copy_(dev_out[c, a:b], non_blocking=True)
-        return dev_out
+        finished = torch.cuda.Event()
+        finished.record(self.copy_stream)
+        return dev_out, finished
 
     def interpolate_points(self, queries: "PTVEngine", method="idw", k=50, idw_power=2.0, smoothing=0.0,
                            out_dtype=torch.float32, return_knn=False, values=True, rbf_kernel="thin_plate_spline"):

@@ -114,8 +114,11 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
         return _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,
                                       idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn, rbf_kernel)
     x, y, z = axes
-    pts = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev)
-    vals = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
+    from . import hostmem
+    # particle table: pageable NumPy -> pinned staging chunks -> HBM (the table and the axes are small next
+    # to the mask and the result)
+    pts = hostmem.stage_to_device(np.ascontiguousarray(points, dtype=np.float64), dev)
+    vals = hostmem.stage_to_device(np.ascontiguousarray(values, dtype=np.float64), dev)
     k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors, "linear": 4}[method]
     if method == "rbf":
         k = min(int(k), len(points))  # scipy _rbfinterp.py:313 clamps silently
@@ -123,19 +126,34 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     ax = [torch.from_numpy(np.array(a, dtype=np.float64)).to(dev) for a in (x, y, z)]
     m = None
     if mask is not None:
-        m = torch.from_numpy(np.ascontiguousarray(mask).astype(np.uint8, copy=False)).to(dev)
+        mh = np.ascontiguousarray(mask)
+        if mh.dtype != np.bool_ and mh.dtype != np.uint8:
+            mh = mh != 0
+        m = hostmem.stage_to_device(mh, dev)
     tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
     kw = dict(method=method, k=int(k), idw_power=float(idw_power), smoothing=float(smoothing), rbf_kernel=rbf_kernel)
     if return_knn:
         out, kd, ki = eng.interpolate(ax[0], ax[1], ax[2], mask=m, out_dtype=tdt, return_knn=True, **kw)
         host = out.cpu().numpy()
         return host[0], host[1], host[2], kd.cpu().numpy(), ki.cpu().numpy()
-    # pinned result buffer, filled chunk by chunk while later z-chunks are still being searched
-    host_t = torch.empty((3, len(z), len(y), len(x)), dtype=tdt, pin_memory=True)
-    eng.interpolate_to_host(ax[0], ax[1], ax[2], host_t, mask=m, **kw)
-    torch.cuda.synchronize(dev)
-    host = host_t.numpy()
+    # pinned result buffer from the pool (cudaHostAlloc of a 1024^3 result costs seconds), filled chunk by
+    # chunk while later z-chunks are still being searched; it goes back to the pool when the caller has
+    # dropped U, V and W
+    shape = (3, len(z), len(y), len(x))
+    host_t = hostmem.results.take(shape, tdt)
+    dkey = (shape, tdt, dev.index)
+    dev_out = _dev_results.pop(dkey, None)
+    if dev_out is None:
+        dev_out = torch.empty(shape, dtype=tdt, device=dev)
+    _, finished = eng.interpolate_to_host(ax[0], ax[1], ax[2], host_t, mask=m, dev_out=dev_out, **kw)
+    finished.synchronize()
+    _dev_results.clear()  # keep at most one device result buffer alive between calls
+    _dev_results[dkey] = dev_out
+    host = hostmem.results.as_numpy(host_t)
     return host[0], host[1], host[2]
+
+
+_dev_results = {}
 
 
 def _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,

@@ -13,11 +13,12 @@ __all__ = ["compute_consistent_divergence", "calculate_flux_xy", "calculate_flux
 
 
 def _to_dev(a, eng, dtype=None):
-    import torch
+    """Pageable NumPy array -> device tensor through the cached pinned staging chunks (hostmem.py)."""
+    from . import hostmem
     a = np.ascontiguousarray(a)
     if dtype is not None:
         a = a.astype(dtype, copy=False)
-    return torch.from_numpy(a).to(eng.device)
+    return hostmem.stage_to_device(a, eng.device)
 
 
 def _field_dtype(*arrs):
