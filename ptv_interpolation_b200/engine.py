@@ -147,13 +147,17 @@ class PTVEngine:
             return out, kd, ki
         return out
 
-    def interpolate_to_host(self, ax_x, ax_y, ax_z, host_out, mask=None, dev_out=None, chunks=None, **kw):
+    def interpolate_to_host(self, ax_x, ax_y, ax_z, host_out, mask=None, dev_out=None, chunks=None, mask_host=None,
+                            **kw):
         """interpolate() with the device->host copy of U,V,W overlapped with the search: the slab is
         processed in z-chunks on the current stream while a second stream drains finished chunks into
         ``host_out`` (a pinned (3,nz,ny,nx) CPU tensor) -- one copy per chunk and component, each a
         contiguous block.  Returns (device tensor, completion event): ``host_out`` may be read after
         ``event.synchronize()``.  A ``dev_out`` given by the caller may be reused for the next frame at
-        once: the main stream waits for the previous drain before the first kernel overwrites it."""
+        once: the main stream waits for the previous drain before the first kernel overwrites it.
+        ``mask_host`` (a C-contiguous bool/uint8 (nz,ny,nx) NumPy array in ordinary host memory) may be given
+        instead of ``mask``: each z-chunk of it is staged to the device right before that chunk is searched,
+        i.e. while the previous chunk's kernel runs."""
         nx, ny, nz = ax_x.numel(), ax_y.numel(), ax_z.numel()
         if dev_out is None:
             dev_out = torch.empty((3, nz, ny, nx), dtype=host_out.dtype, device=self.device)
@@ -169,9 +173,24 @@ class PTVEngine:
         # the drain runs on copy_stream: keep the block out of the caching allocator until it is done
         dev_out.record_stream(self.copy_stream)
         cuts = [round(i * nz / chunks) for i in range(chunks + 1)]
+        if mask_host is not None:
+            from . import hostmem
+            if tuple(mask_host.shape) != (nz, ny, nx):
+                raise ValueError("mask must have shape (nz, ny, nx)")
+            key = (nz, ny, nx)
+            if getattr(self, "_mask_dev_key", None) != key:
+                self._mask_dev = torch.empty(key, dtype=torch.uint8, device=self.device)
+                self._mask_dev_key = key
+            mask = self._mask_dev
+            if not hasattr(self, "in_stream"):
+                self.in_stream = torch.cuda.Stream(device=self.device)
+            self.in_stream.wait_stream(main)  # earlier kernels may still read the device mask
         for a, b in zip(cuts[:-1], cuts[1:]):
             if b <= a:
                 continue
+            if mask_host is not None:  # DMA on the input stream: it overlaps the previous chunk's kernel
+                hostmem.stage_to_device(mask_host[a:b], self.device, out=mask[a:b], stream=self.in_stream)
+                main.wait_stream(self.in_stream)
             self.interpolate(ax_x, ax_y, ax_z[a:b], mask=None if mask is None else mask[a:b],
                              out=dev_out[:, a:b], **kw)
             done = torch.cuda.Event()

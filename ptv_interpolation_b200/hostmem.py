@@ -33,10 +33,10 @@ def _staging_for(dev):
         return _staging[key]
 
 
-def stage_to_device(arr, dev, out=None):
+def stage_to_device(arr, dev, out=None, stream=None):
     """Copy a C-contiguous NumPy array to a (new or given) device tensor of the same shape/dtype through
-    the pinned staging chunks.  Asynchronous with respect to the current stream's later work only: returns
-    when the last chunk's DMA has been ENQUEUED and the host array has been fully read."""
+    the pinned staging chunks; the DMAs run on ``stream`` (default: the current stream).  Returns when the
+    host array has been fully read and the last DMA has completed."""
     arr = np.ascontiguousarray(arr)
     t_host = torch.from_numpy(arr.view(np.uint8).reshape(-1)) if arr.dtype == np.bool_ else \
         torch.from_numpy(arr.reshape(-1).view(np.uint8))
@@ -48,7 +48,8 @@ def stage_to_device(arr, dev, out=None):
     if nbytes == 0:
         return out
     bufs, evs = _staging_for(dev)
-    stream = torch.cuda.current_stream(dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
     used = [False, False]
     for i, off in enumerate(range(0, nbytes, _CHUNK_BYTES)):
         b = i & 1
@@ -56,7 +57,8 @@ def stage_to_device(arr, dev, out=None):
         if used[b]:
             evs[b].synchronize()  # the DMA that last read this chunk has finished
         bufs[b][:n].copy_(t_host[off:off + n])  # host -> pinned (torch's CPU thread pool)
-        dflat[off:off + n].copy_(bufs[b][:n], non_blocking=True)
+        with torch.cuda.stream(stream):
+            dflat[off:off + n].copy_(bufs[b][:n], non_blocking=True)
         evs[b].record(stream)
         used[b] = True
     for b in range(2):  # the chunks are shared by later calls on other streams

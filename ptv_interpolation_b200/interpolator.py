@@ -99,8 +99,6 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     """interpolator.py:65-203.  ``n_jobs`` is accepted and ignored (one GPU does the work).
     Returns (U, V, W): three writable (nz, ny, nx) views of one host array, like the reference."""
     import torch
-    points = df[["x", "y", "z"]].values
-    values = df[["u", "v", "w"]].values
     if method not in _GPU_METHODS:
         # interpolator.py:197 hands every other name to griddata, which knows 'cubic' only in 1-D / 2-D
         raise ValueError(f"Unknown interpolation method {method!r} for 3 dimensional data")
@@ -111,25 +109,30 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     eng = default_engine(device)
     dev = eng.device
     if axes is None:
+        points = df[["x", "y", "z"]].values  # interpolator.py:78-79
+        values = df[["u", "v", "w"]].values
         return _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,
                                       idw_neighbors, sibson_neighbors, mask, out_dtype, return_knn, rbf_kernel)
     x, y, z = axes
     from . import hostmem
-    # particle table: pageable NumPy -> pinned staging chunks -> HBM (the table and the axes are small next
-    # to the mask and the result)
-    pts = hostmem.stage_to_device(np.ascontiguousarray(points, dtype=np.float64), dev)
-    vals = hostmem.stage_to_device(np.ascontiguousarray(values, dtype=np.float64), dev)
+    # particle table (interpolator.py:78-79): the six columns go to the device one by one through the pinned
+    # staging chunks and are interleaved into (Np,3) rows THERE -- df[[...]].values would transpose 2 x 24 B
+    # per particle on one host core first
+    pts = _columns_to_device(df, ("x", "y", "z"), dev)
+    vals = _columns_to_device(df, ("u", "v", "w"), dev)
+    npart = pts.shape[0]
     k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors, "linear": 4}[method]
     if method == "rbf":
-        k = min(int(k), len(points))  # scipy _rbfinterp.py:313 clamps silently
+        k = min(int(k), npart)  # scipy _rbfinterp.py:313 clamps silently
     eng.build(pts, vals)
     ax = [torch.from_numpy(np.array(a, dtype=np.float64)).to(dev) for a in (x, y, z)]
-    m = None
+    m = mh = None
     if mask is not None:
         mh = np.ascontiguousarray(mask)
         if mh.dtype != np.bool_ and mh.dtype != np.uint8:
             mh = mh != 0
-        m = hostmem.stage_to_device(mh, dev)
+        if return_knn:
+            m = hostmem.stage_to_device(mh, dev)
     tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
     kw = dict(method=method, k=int(k), idw_power=float(idw_power), smoothing=float(smoothing), rbf_kernel=rbf_kernel)
     if return_knn:
@@ -145,7 +148,8 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     dev_out = _dev_results.pop(dkey, None)
     if dev_out is None:
         dev_out = torch.empty(shape, dtype=tdt, device=dev)
-    _, finished = eng.interpolate_to_host(ax[0], ax[1], ax[2], host_t, mask=m, dev_out=dev_out, **kw)
+    # the mask enters z-chunk by z-chunk, each chunk staged while the previous one is being searched
+    _, finished = eng.interpolate_to_host(ax[0], ax[1], ax[2], host_t, mask_host=mh, dev_out=dev_out, **kw)
     finished.synchronize()
     _dev_results.clear()  # keep at most one device result buffer alive between calls
     _dev_results[dkey] = dev_out
@@ -154,6 +158,17 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
 
 
 _dev_results = {}
+
+
+def _columns_to_device(df, cols, dev):
+    """(Np, len(cols)) float64 device tensor of the DataFrame's columns, rows interleaved on the device."""
+    import torch
+    from . import hostmem
+    out = torch.empty((len(df), len(cols)), dtype=torch.float64, device=dev)
+    for j, c in enumerate(cols):
+        col = np.ascontiguousarray(df[c].to_numpy(dtype=np.float64, copy=False))
+        out[:, j] = hostmem.stage_to_device(col, dev)
+    return out
 
 
 def _interpolate_scattered(eng, points, values, grid_tuple, method, rbf_neighbors, smoothing, idw_power,
