@@ -391,23 +391,15 @@ def run_b200(args):
 
     def step(record):
         e = [ev() for _ in range(4)] if record else None
+        marks = {"built": 1, "interpolated": 2}
         if record:
             e[0].record()
-        eng.build(points, values)
-        if record:
-            e[1].record()
-        uvw = eng.interpolate(ax, ax, ax[z0:z1], mask=mask_slab, method=method, k=k, out=out)
-        if record:
-            e[2].record()
-        halos = comm.exchange_halos(uvw[2], mask_slab)
-        div, stats, q_xy, q_xz, q_yz = eng.divergence_flux(uvw[0], uvw[1], uvw[2], mask_slab, 1.0, 1.0, 1.0,
-                                                           w_below=halos[0], w_above=halos[1], mask_above=halos[2])
-        comm.reduce_sum_(q_xz, q_yz, stats)
-        q_xy = comm.gather_planes(q_xy)
+        res = hot_path_step(eng, points, values, ax, ax, ax, mask_slab, comm, method=method, k=k, out=out,
+                            mark=(lambda label: e[marks[label]].record()) if record else None)
         if record:
             e[3].record()
-        keep.update(div=div, halos=halos)
-        return e, stats
+        keep.update(div=res.div, res=res)
+        return e, (res.mean_abs_div * res.n_fluid, res.n_fluid)
 
     for _ in range(args.warmup):
         step(False)
@@ -461,8 +453,9 @@ def run_b200(args):
     if not args.no_parity:
         from scipy.spatial import KDTree
         tree = KDTree(points_np)
+        halos = comm.exchange_halos(out[2], mask_slab)  # the planes the timed step used (again, for the check)
         parity = parity_check(dict(method=method, k=k), points_np, values_np, tree, ax_np, z0, z1, mask_slab_np, out,
-                              keep.get("div"), keep.get("halos"), args.parity_voxels, seed=100 + rank)
+                              keep.get("div"), halos, args.parity_voxels, seed=100 + rank)
         if world > 1:
             gathered = [None] * world
             dist.all_gather_object(gathered, parity)

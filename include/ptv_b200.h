@@ -86,6 +86,16 @@ int ptv_hash_destroy(ptv_hash* h);
  * d_values: (n,3) float64 rows (u,v,w) == df[['u','v','w']].values (interpolator.py:79).
  * cell_size <= 0 picks the cell edge from the particle density.  Buffers owned by the
  * handle are reused across builds (time-resolved sweeps rebuild per frame).            */
+/* Slab hash for the z-slab sharding of SURVEY.md 8(e) (no counterpart in the reference, whose only parallel
+ * split is interpolator.py:176-182): the same build, but only particles with
+ *   z_lo - halo <= z <= z_hi + halo,  halo = halo_factor x (3 k / (4 pi rho))^(1/3),  rho = n / bbox volume
+ * are binned -- a rank that interpolates the planes [z_lo, z_hi] bins its slab's particles plus a halo instead
+ * of the whole cloud.  Searches stay exact: ptv_knn_interp counts every voxel whose k-th distance reaches
+ * outside the binned range (ptv_hash_clip_violations, synchronises); if the count is not zero the caller
+ * repeats the frame on the full hash.  method = PTV_METHOD_LINEAR is refused on a slab hash. */
+int ptv_hash_build_slab(ptv_hash* h, const double* d_points, const double* d_values, int64_t n, double cell_size,
+                        double z_lo, double z_hi, int k, double halo_factor, void* stream);
+int ptv_hash_clip_violations(const ptv_hash* h, int64_t* count);
 int ptv_hash_build(ptv_hash* h, const double* d_points, const double* d_values, int64_t n,
                    double cell_size, void* stream);
 int ptv_hash_info(const ptv_hash* h, int64_t* n, int dims[3], double origin[3], double* cell_size,

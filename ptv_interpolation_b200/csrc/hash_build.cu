@@ -87,13 +87,19 @@ __device__ __forceinline__ int cell_coord(double p, double o, double inv_cell, i
 __global__ void __launch_bounds__(256) cell_count_kernel(const double* __restrict__ pts, int64_t n,
                                                           double ox, double oy, double oz,
                                                           double inv_cell, int cnx, int cny, int cnz,
+                                                          double zlo, double zhi,
                                                           int32_t* __restrict__ cid,
                                                           int32_t* __restrict__ counts) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const double pz = pts[i * 3 + 2];
+  if (pz < zlo || pz > zhi) {  // slab hash: outside the binned z-range
+    cid[i] = -1;
+    return;
+  }
   const int cx = cell_coord(pts[i * 3 + 0], ox, inv_cell, cnx);
   const int cy = cell_coord(pts[i * 3 + 1], oy, inv_cell, cny);
-  const int cz = cell_coord(pts[i * 3 + 2], oz, inv_cell, cnz);
+  const int cz = cell_coord(pz, oz, inv_cell, cnz);
   const int32_t c = (cz * cny + cy) * cnx + cx;
   cid[i] = c;
   atomicAdd(&counts[c], 1);
@@ -177,6 +183,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict_
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int32_t c = cid[i];
+  if (c < 0) return;
   const int32_t pos = cell_start[c] + atomicAdd(&cell_fill[c], 1);
   sorted_idx[pos] = (int32_t)i;
 }
@@ -239,11 +246,12 @@ __global__ void __launch_bounds__(256) cell_canonical_kernel(const int32_t* __re
 __global__ void __launch_bounds__(256) fill_records_kernel(const double* __restrict__ pts,
                                                             const double* __restrict__ vals_in,
                                                             const int32_t* __restrict__ sorted_idx,
-                                                            int64_t n, ParticleRec* __restrict__ rec,
+                                                            int64_t n, const int32_t* __restrict__ n_binned,
+                                                            ParticleRec* __restrict__ rec,
                                                             Value4* __restrict__ vals_s64,
                                                             float4* __restrict__ vals_s32) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+  if (p >= n || p >= *n_binned) return;  // slab hash: fewer than n particles are binned
   const int32_t i = sorted_idx[p];
   ParticleRec r;
   r.x = pts[(int64_t)i * 3 + 0];
@@ -342,6 +350,8 @@ ptv::HashGrid ptv_hash::view() const {
   g.cell = cell; g.inv_cell = 1.0 / cell;
   g.cnx = dims[0]; g.cny = dims[1]; g.cnz = dims[2];
   g.n = n;
+  g.clip_lo = clip_lo;
+  g.clip_hi = clip_hi;
   return g;
 }
 
@@ -373,6 +383,7 @@ extern "C" int ptv_hash_destroy(ptv_hash* h) {
   cudaFree(h->fail_list);
   cudaFree(h->fail_count);
   cudaFree(h->fail_flags);
+  cudaFree(h->clip_count);
   cudaFree(h->hull_rec);
   cudaFree(h->hull_box);
   cudaFree(h->hull_rec2);
@@ -384,8 +395,34 @@ extern "C" int ptv_hash_destroy(ptv_hash* h) {
   return PTV_OK;
 }
 
+static int build_impl(ptv_hash* h, const double* d_points, const double* d_values, int64_t n, double cell_size,
+                      bool slab, double z_lo, double z_hi, int k, double halo_factor, void* stream_);
+
 extern "C" int ptv_hash_build(ptv_hash* h, const double* d_points, const double* d_values, int64_t n,
                               double cell_size, void* stream_) {
+  return build_impl(h, d_points, d_values, n, cell_size, false, 0.0, 0.0, 0, 0.0, stream_);
+}
+
+extern "C" int ptv_hash_build_slab(ptv_hash* h, const double* d_points, const double* d_values, int64_t n,
+                                   double cell_size, double z_lo, double z_hi, int k, double halo_factor,
+                                   void* stream_) {
+  if (!(z_hi >= z_lo) || k < 1 || !(halo_factor > 0.0)) {
+    set_error("ptv_hash_build_slab: need z_lo <= z_hi, k >= 1, halo_factor > 0");
+    return PTV_ERR_INVALID;
+  }
+  return build_impl(h, d_points, d_values, n, cell_size, true, z_lo, z_hi, k, halo_factor, stream_);
+}
+
+extern "C" int ptv_hash_clip_violations(const ptv_hash* h, int64_t* count) {
+  if (!h || !count) { set_error("ptv_hash_clip_violations: NULL argument"); return PTV_ERR_INVALID; }
+  int c = 0;
+  if (h->clip_count != nullptr) PTV_CUDA(cudaMemcpy(&c, h->clip_count, sizeof(int), cudaMemcpyDeviceToHost));
+  *count = c;
+  return PTV_OK;
+}
+
+static int build_impl(ptv_hash* h, const double* d_points, const double* d_values, int64_t n, double cell_size,
+                      bool slab, double z_lo, double z_hi, int k, double halo_factor, void* stream_) {
   if (!h || !d_points || !d_values) { set_error("ptv_hash_build: NULL argument"); return PTV_ERR_INVALID; }
   if (n <= 0) { set_error("ptv_hash_build: no particles"); return PTV_ERR_TOO_FEW; }
   if (n >= (int64_t)2147483000) { set_error("ptv_hash_build: more than 2^31 particles"); return PTV_ERR_INVALID; }
@@ -409,6 +446,23 @@ extern "C" int ptv_hash_build(ptv_hash* h, const double* d_points, const double*
   double cell;
   int dims[3];
   choose_cells(h->bbox_host, n, cell_size, tuning().ppc, dims, &cell);
+  // slab hash: bin only z in [z_lo - halo, z_hi + halo], halo = halo_factor x the radius expected to hold k
+  // particles at the cloud's mean density; the cell edge stays the one of the whole cloud
+  double zlo = -INFINITY, zhi = INFINITY;
+  h->clip_lo = -INFINITY;
+  h->clip_hi = INFINITY;
+  if (slab) {
+    double vol = 1.0;
+    for (int c = 0; c < 3; ++c) vol *= std::max(h->bbox_host[3 + c] - h->bbox_host[c], cell);
+    const double halo = halo_factor * std::cbrt(0.238732414637843 * k * vol / (double)n);
+    zlo = z_lo - halo;
+    zhi = z_hi + halo;
+    if (zlo > h->bbox_host[2]) { h->clip_lo = zlo; h->bbox_host[2] = std::min(zlo, h->bbox_host[5]); } else zlo = -INFINITY;
+    if (zhi < h->bbox_host[5]) { h->clip_hi = zhi; h->bbox_host[5] = std::max(zhi, h->bbox_host[2]); } else zhi = INFINITY;
+    dims[2] = (int)std::max(1.0, std::floor((h->bbox_host[5] - h->bbox_host[2]) / cell) + 1.0);
+  }
+  if (h->clip_count == nullptr) PTV_CUDA(cudaMalloc(&h->clip_count, sizeof(int)));
+  PTV_CUDA(cudaMemsetAsync(h->clip_count, 0, sizeof(int), stream));
   const int64_t ncells = (int64_t)dims[0] * dims[1] * dims[2];
   int rc = ensure_capacity(h, n, ncells);
   if (rc != PTV_OK) return rc;
@@ -422,7 +476,7 @@ extern "C" int ptv_hash_build(ptv_hash* h, const double* d_points, const double*
   PTV_CUDA(cudaMemsetAsync(h->cell_fill, 0, (ncells + 1) * sizeof(int32_t), stream));
   const int nb_p = (int)((n + 255) / 256);
   cell_count_kernel<<<nb_p, 256, 0, stream>>>(d_points, n, h->origin[0], h->origin[1], h->origin[2],
-                                              1.0 / cell, dims[0], dims[1], dims[2], h->cid, h->cell_start);
+                                              1.0 / cell, dims[0], dims[1], dims[2], zlo, zhi, h->cid, h->cell_start);
   // 3. exclusive scan over ncells+1 entries (last entry becomes n)
   const int64_t nscan = ncells + 1;
   const int nb_s = (int)((nscan + kScanTile - 1) / kScanTile);
@@ -434,7 +488,8 @@ extern "C" int ptv_hash_build(ptv_hash* h, const double* d_points, const double*
   int32_t* max_count = h->cell_fill + ncells;  // zeroed above
   cell_canonical_kernel<<<(int)((ncells + 255) / 256), 256, 0, stream>>>(h->cell_start, ncells,
                                                                         h->sorted_idx, max_count);
-  fill_records_kernel<<<nb_p, 256, 0, stream>>>(d_points, d_values, h->sorted_idx, n, h->rec, h->vals_s64, h->vals_s32);
+  fill_records_kernel<<<nb_p, 256, 0, stream>>>(d_points, d_values, h->sorted_idx, n, h->cell_start + ncells, h->rec,
+                                                h->vals_s64, h->vals_s32);
   fill_values_kernel<<<nb_p, 256, 0, stream>>>(d_values, n, h->vals);
   count_launches(8);
   PTV_CUDA(cudaGetLastError());

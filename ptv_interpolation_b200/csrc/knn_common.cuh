@@ -30,6 +30,7 @@ struct KnnParams {
   int rbf_kernel;  // 0 thin_plate_spline, 1 cubic, 2 linear, 3 quintic
   int rbf_npoly;   // monomials of the polynomial tail: 4 (degree 1), 1 (degree 0), 10 (degree 2)
   int* err_flag;
+  int* clip_count;  // slab hash: voxels whose certified radius reaches outside the binned z-range
   // stream kernel -> heap kernel hand-off: tiles the optimistic kernel could not finish
   int* fail_list;        // [capacity]
   int* fail_count;       // [1]

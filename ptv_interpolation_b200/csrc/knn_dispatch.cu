@@ -114,6 +114,10 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
                               void* d_w, int64_t* d_knn_idx, double* d_knn_dist, void* stream_) {
   ptv_hash* h = const_cast<ptv_hash*>(hc);  // scratch buffers of the handle are grown on demand
   if (!h || !h->built) { set_error("ptv_knn_interp: hash not built"); return PTV_ERR_INVALID; }
+  if (method == PTV_METHOD_LINEAR && (h->clip_lo > -INFINITY || h->clip_hi < INFINITY)) {
+    set_error("ptv_knn_interp: method='linear' needs the full hash (ptv_hash_build), not a slab hash");
+    return PTV_ERR_INVALID;
+  }
   if (!d_ax_x || !d_ax_y || !d_ax_z || !d_u || !d_v || !d_w) { set_error("ptv_knn_interp: NULL argument"); return PTV_ERR_INVALID; }
   if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_knn_interp: empty grid"); return PTV_ERR_INVALID; }
   if ((d_knn_idx == nullptr) != (d_knn_dist == nullptr)) { set_error("ptv_knn_interp: knn_idx and knn_dist must be given together"); return PTV_ERR_INVALID; }
@@ -155,6 +159,7 @@ extern "C" int ptv_knn_interp(const ptv_hash* hc, const double* d_ax_x, int nx, 
   p.rbf_npoly = rbf_npoly;
   p.rscale = tuning().rscale;
   p.err_flag = h->err_flag;
+  p.clip_count = h->clip_count;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.fail_flags = nullptr; p.fail_tx = p.fail_ty = p.fail_tz = 1;
   p.qrec = nullptr; p.nq = 0; p.keep = nullptr; p.kth_dist = nullptr; p.mad_threshold = 0.0;
@@ -237,6 +242,7 @@ static void init_point_params(KnnParams& p, const ptv_hash* h, const ptv_hash* q
   p.rbf_kernel = 0;
   p.rbf_npoly = 4;
   p.err_flag = h->err_flag;
+  p.clip_count = h->clip_count;
   p.fail_list = nullptr; p.fail_count = nullptr; p.tile_list = nullptr; p.tile_count = nullptr; p.stats = nullptr;
   p.fail_flags = nullptr; p.fail_tx = p.fail_ty = p.fail_tz = 1;
   p.qrec = q->rec; p.nq = q->n;

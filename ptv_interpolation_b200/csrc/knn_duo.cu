@@ -818,6 +818,18 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
         if (ok[v]) { e_lo[v] = th[v].e_lo; e_hi[v] = th[v].e_hi; }
     }
     if (!__any_sync(kFull, ok[0] || ok[1])) continue;
+    // slab hash: the neighbours are certified only if every key below E_hi belongs to a binned particle,
+    // i.e. the k-th distance stays inside the binned z-range; otherwise the caller redoes the frame on the
+    // full hash (pipeline.hot_path_step)
+    if (g.clip_lo > -INFINITY || g.clip_hi < INFINITY) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        if (ok[v]) {
+          const double dmin = fmin(qz[v] - g.clip_lo, g.clip_hi - qz[v]);
+          if (!(dmin > 0.0 && e_hi[v] <= dmin * dmin)) atomicAdd(p.clip_count, 1);
+        }
+      }
+    }
     __syncwarp();  // the histograms are dead: the columns now hold the lists
 
     // ---- phase B: exact classification of the final region

@@ -374,6 +374,11 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
 
   const int kk = count;  // == k whenever Np >= k (checked on the host)
   double su = 0.0, sv = 0.0, sw = 0.0;
+  // slab hash: certified only if the k-th distance stays inside the binned z-range (see knn_duo.cu)
+  if (active && p.clip_count != nullptr && (g.clip_lo > -INFINITY || g.clip_hi < INFINITY)) {
+    const double dmin = fmin(qz - g.clip_lo, g.clip_hi - qz);
+    if (!(count >= k && dmin > 0.0 && thr <= dmin * dmin)) atomicAdd(p.clip_count, 1);
+  }
 
   if (kRbf) {
     // every lane of the warp helps to solve each voxel's local system, so no early exits here

@@ -32,6 +32,9 @@ struct HashGrid {  // plain-old-data view passed to kernels by value
   double cell, inv_cell;
   int cnx, cny, cnz;
   int64_t n;
+  // slab hash (ptv_hash_build_slab): only particles with clip_lo <= z <= clip_hi are binned; a voxel's
+  // neighbours are certified only if its k-th distance stays inside that range (+-INFINITY = side not clipped)
+  double clip_lo, clip_hi;
 };
 
 void set_error(const std::string& msg);
@@ -94,6 +97,8 @@ struct ptv_hash {
   int hull_n = 0;
   bool hull_valid = false;
   bool last_used_stream = false;
+  double clip_lo = -1.0 / 0.0, clip_hi = 1.0 / 0.0;  // z-range of the binned particles (slab hash)
+  int* clip_count = nullptr;                          // device: voxels whose search left the range
   int64_t last_stage_counts[2] = {0, 0};
   int64_t cap_n = 0;
   int64_t cap_cells = 0;

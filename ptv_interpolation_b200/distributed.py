@@ -39,14 +39,19 @@ class SlabComm:
     def exchange_halos(self, w_slab: torch.Tensor, mask_slab: torch.Tensor):
         """Returns (w_below, w_above, mask_above): the (ny,nx) planes z0-1 and z1 owned by the
         z-neighbours (None at the domain edges -> Neumann edge rule of physics.py:38-45)."""
+        return self.wait_halos(self.post_halos(w_slab[0], w_slab[-1], mask_slab[0]))
+
+    def post_halos(self, first_w: torch.Tensor, last_w: torch.Tensor, first_m: torch.Tensor):
+        """Start the halo exchange as soon as the slab's first and last planes exist (the planes in between
+        may still be being interpolated); wait_halos() returns the neighbours' planes."""
         if self.world == 1:
-            return None, None, None
+            return None
         if self.z1 - self.z0 < 1:
             raise ValueError("every rank must own at least one z-plane")
         ops, w_below, w_above, m_above = [], None, None, None
-        first_w = w_slab[0].contiguous()
-        last_w = w_slab[-1].contiguous()
-        first_m = mask_slab[0].contiguous()
+        first_w = first_w.contiguous()
+        last_w = last_w.contiguous()
+        first_m = first_m.contiguous()
         if self.lower is not None:  # my first plane is the lower neighbour's "above"
             w_below = torch.empty_like(first_w)
             ops += [dist.P2POp(dist.isend, first_w, self.lower, self.group),
@@ -58,9 +63,22 @@ class SlabComm:
             ops += [dist.P2POp(dist.isend, last_w, self.upper, self.group),
                     dist.P2POp(dist.irecv, w_above, self.upper, self.group),
                     dist.P2POp(dist.irecv, m_above, self.upper, self.group)]
-        for req in dist.batch_isend_irecv(ops):
+        reqs = dist.batch_isend_irecv(ops)
+        return reqs, (w_below, w_above, m_above), (first_w, last_w, first_m)  # the send buffers stay alive
+
+    def wait_halos(self, handle):
+        if handle is None:
+            return None, None, None
+        for req in handle[0]:
             req.wait()
-        return w_below, w_above, m_above
+        return handle[1]
+
+    def reduce_profiles_(self, acc: torch.Tensor):
+        """ONE sum-all-reduce for everything the stencil pass accumulates: ``acc`` is the flat float64 buffer
+        [sum|div|, n_fluid | Q_xy[nz] (each rank fills its own planes, zeros elsewhere) | Q_xz[ny] | Q_yz[nx]]."""
+        if self.world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        return acc
 
     def reduce_sum_(self, *tensors):
         """In-place SUM all-reduce of small float64 tensors (flux profiles, statistics)."""

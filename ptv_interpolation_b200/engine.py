@@ -97,6 +97,30 @@ class PTVEngine:
         self._keep = (points, values)
         self.n_particles = points.shape[0]
 
+    def build_slab(self, points: torch.Tensor, values: torch.Tensor, z_lo: float, z_hi: float, k: int,
+                   halo_factor: float = 2.5, cell_size: float = 0.0):
+        """build() restricted to the particles a rank needs for the planes z_lo..z_hi: its slab plus a halo of
+        ``halo_factor`` expected k-neighbour radii.  After interpolating, ``clip_violations()`` must be 0 --
+        otherwise some search left the binned range and the frame has to be redone after a full build()."""
+        if points.dtype != torch.float64 or values.dtype != torch.float64:
+            raise ValueError("points and values must be float64")
+        points = points.contiguous()
+        values = values.contiguous()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_hash_build_slab(self._h, _ptr(points), _ptr(values), points.shape[0],
+                                                     float(cell_size), float(z_lo), float(z_hi), int(k),
+                                                     float(halo_factor), self._stream()))
+        self._keep = (points, values)
+        self.n_particles = points.shape[0]
+
+    def clip_violations(self) -> int:
+        """Voxels of the interpolate() calls since the last build whose k-th distance reached outside the
+        z-range a slab hash binned (0 on a full hash).  Synchronises the device."""
+        c = C.c_int64()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_hash_clip_violations(self._h, C.byref(c)))
+        return int(c.value)
+
     def hash_info(self):
         n = C.c_int64()
         dims = (C.c_int * 3)()
@@ -317,8 +341,12 @@ class PTVEngine:
                                                 self._stream()))
         return (div, stats) if with_stats else div
 
-    def divergence_flux(self, u, v, w, mask, dx, dy, dz, w_below=None, w_above=None, mask_above=None):
-        """One pass: (div, stats[2] = (sum|div| over fluid, n_fluid), q_xy[nz], q_xz[ny], q_yz[nx])."""
+    def divergence_flux(self, u, v, w, mask, dx, dy, dz, w_below=None, w_above=None, mask_above=None, z0=0,
+                        nz_global=None):
+        """One pass: (div, stats[2] = (sum|div| over fluid, n_fluid), q_xy[nz], q_xz[ny], q_yz[nx]).
+        With ``nz_global`` the accumulators live in one flat buffer laid out for the whole grid -- Q_xy of
+        this slab at planes z0.. -- so that a single all-reduce finishes all of them (returned as the sixth
+        value; q_xy is then the full-length profile)."""
         nz, ny, nx = u.shape
         if mask.dtype == torch.bool:
             mask = mask.view(torch.uint8)
@@ -326,14 +354,17 @@ class PTVEngine:
             mask_above = mask_above.view(torch.uint8)
         u, v, w, mask = u.contiguous(), v.contiguous(), w.contiguous(), mask.contiguous()
         div = torch.empty_like(u)
-        acc = torch.zeros(2 + nz + ny + nx, dtype=torch.float64, device=self.device)
-        stats, qxy, qxz, qyz = acc[:2], acc[2:2 + nz], acc[2 + nz:2 + nz + ny], acc[2 + nz + ny:]
+        nzg = nz if nz_global is None else int(nz_global)
+        acc = torch.zeros(2 + nzg + ny + nx, dtype=torch.float64, device=self.device)
+        stats, qxy, qxz, qyz = acc[:2], acc[2:2 + nzg], acc[2 + nzg:2 + nzg + ny], acc[2 + nzg + ny:]
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.ptv_divergence_flux(_ptr(u), _ptr(v), _ptr(w), _ptr(mask), nx, ny, nz, float(dx),
                                                      float(dy), float(dz), _ptr(w_below), _ptr(w_above),
                                                      _ptr(mask_above), _dtype_code(u.dtype), _ptr(div), _ptr(stats),
-                                                     _ptr(qxy), _ptr(qxz), _ptr(qyz), self._stream()))
-        return div, stats, qxy, qxz, qyz
+                                                     _ptr(qxy[z0:z0 + nz]), _ptr(qxz), _ptr(qyz), self._stream()))
+        if nz_global is None:
+            return div, stats, qxy, qxz, qyz
+        return div, stats, qxy, qxz, qyz, acc
 
     def strain_vorticity(self, u, v, w, dx, dy, dz, mask=None, strain=True, vorticity=True):
         """(shear-rate magnitude, vorticity magnitude) of the field; either may be skipped (None)."""

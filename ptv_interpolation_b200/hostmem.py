@@ -13,6 +13,7 @@ functions need are kept and reused:
 from __future__ import annotations
 
 import threading
+import warnings
 import weakref
 
 import numpy as np
@@ -38,8 +39,10 @@ def stage_to_device(arr, dev, out=None, stream=None):
     the pinned staging chunks; the DMAs run on ``stream`` (default: the current stream).  Returns when the
     host array has been fully read and the last DMA has completed."""
     arr = np.ascontiguousarray(arr)
-    t_host = torch.from_numpy(arr.view(np.uint8).reshape(-1)) if arr.dtype == np.bool_ else \
-        torch.from_numpy(arr.reshape(-1).view(np.uint8))
+    with warnings.catch_warnings():  # read-only inputs (broadcast views, memory maps) are only read here
+        warnings.simplefilter("ignore", UserWarning)
+        t_host = torch.from_numpy(arr.view(np.uint8).reshape(-1)) if arr.dtype == np.bool_ else \
+            torch.from_numpy(arr.reshape(-1).view(np.uint8))
     nbytes = t_host.numel()
     tdt = torch.from_numpy(np.empty(0, dtype=np.uint8 if arr.dtype == np.bool_ else arr.dtype)).dtype
     if out is None:

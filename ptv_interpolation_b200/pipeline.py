@@ -24,18 +24,53 @@ class StepResult:
 
 def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, comm: SlabComm, method="idw",
                   k=50, idw_power=2.0, spacing=(1.0, 1.0, 1.0), out=None, out_dtype=torch.float32,
-                  rebuild=True) -> StepResult:
+                  rebuild=True, mark=None) -> StepResult:
     """One pass over one PTV frame for this rank's z-slab.  ``ax_z`` is the FULL z axis; the slab is
-    comm.z0:comm.z1.  ``mask_slab`` is the (nz_local, ny, nx) uint8 pore mask of the slab."""
-    if rebuild:
+    comm.z0:comm.z1.  ``mask_slab`` is the (nz_local, ny, nx) uint8 pore mask of the slab.  ``mark(label)``
+    is called after the hash build ("built") and after the last interpolation launch ("interpolated")."""
+    mark = mark or (lambda label: None)
+    slab_hash = rebuild and comm.world > 1 and method in ("idw", "sibson")
+    if slab_hash:
+        # north_star: "each GPU holds its slab's particles plus a halo" -- bin only z within the slab +- a halo
+        # of expected k-neighbour radii; a search that leaves the range is detected below
+        eng.build_slab(points, values, float(ax_z[comm.z0]), float(ax_z[comm.z1 - 1]), k)
+    elif rebuild:
         eng.build(points, values)
+    mark("built")
     az = ax_z[comm.z0:comm.z1]
-    uvw = eng.interpolate(ax_x, ax_y, az, mask=mask_slab, method=method, k=k, idw_power=idw_power,
-                          out_dtype=out_dtype, out=out)
-    w_below, w_above, m_above = comm.exchange_halos(uvw[2], mask_slab)
+    nzl = comm.z1 - comm.z0
+    nx, ny = ax_x.numel(), ax_y.numel()
+    kw = dict(method=method, k=k, idw_power=idw_power)
+    edge = 32  # z-extent of one CTA region of the streaming kernel
+    if comm.world > 1 and nzl >= 3 * edge:
+        # the slab's first and last planes feed the neighbours' divergence stencils: interpolate the two
+        # boundary chunks first, start the halo exchange, and let it travel while the interior is searched
+        if out is None:
+            out = torch.empty((3, nzl, ny, nx), dtype=out_dtype, device=eng.device)
+        for a, b in ((0, edge), (nzl - edge, nzl)):
+            eng.interpolate(ax_x, ax_y, az[a:b], mask=mask_slab[a:b], out=out[:, a:b], **kw)
+        pending = comm.post_halos(out[2, 0], out[2, nzl - 1], mask_slab[0])
+        eng.interpolate(ax_x, ax_y, az[edge:nzl - edge], mask=mask_slab[edge:nzl - edge], out=out[:, edge:nzl - edge], **kw)
+        uvw = out
+        mark("interpolated")
+        w_below, w_above, m_above = comm.wait_halos(pending)
+    else:
+        uvw = eng.interpolate(ax_x, ax_y, az, mask=mask_slab, out_dtype=out_dtype, out=out, **kw)
+        mark("interpolated")
+        w_below, w_above, m_above = comm.exchange_halos(uvw[2], mask_slab)
     dx, dy, dz = spacing
-    div, stats, q_xy, q_xz, q_yz = eng.divergence_flux(uvw[0], uvw[1], uvw[2], mask_slab, dx, dy, dz, w_below=w_below,
-                                                       w_above=w_above, mask_above=m_above)
-    comm.reduce_sum_(q_xz, q_yz, stats)
-    q_xy = comm.gather_planes(q_xy)
+    div, stats, q_xy, q_xz, q_yz, acc = eng.divergence_flux(uvw[0], uvw[1], uvw[2], mask_slab, dx, dy, dz,
+                                                            w_below=w_below, w_above=w_above, mask_above=m_above,
+                                                            z0=comm.z0, nz_global=comm.nz)
+    comm.reduce_profiles_(acc)  # one all-reduce: (sum|div|, n_fluid), Q_xy, Q_xz, Q_yz
+    if slab_hash:
+        # exact fall-back: some voxel's k-th neighbour may lie beyond the halo -> redo the frame on the full
+        # hash, on every rank (the decision is collective so that the halo exchange stays matched)
+        viol = torch.tensor([eng.clip_violations()], dtype=torch.int64, device=eng.device)
+        if comm.on:
+            torch.distributed.all_reduce(viol, op=torch.distributed.ReduceOp.MAX, group=comm.group)
+        if int(viol.item()) > 0:
+            eng.build(points, values)
+            return hot_path_step(eng, points, values, ax_x, ax_y, ax_z, mask_slab, comm, method=method, k=k,
+                                 idw_power=idw_power, spacing=spacing, out=uvw, out_dtype=out_dtype, rebuild=False)
     return StepResult(uvw, div, q_xy, q_xz, q_yz, stats[0] / stats[1], stats[1])

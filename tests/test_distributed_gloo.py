@@ -76,6 +76,24 @@ def _worker(rank, world, port, shape, tmp):
         assert np.allclose(q_xz.numpy(), v.sum(axis=(0, 2)), rtol=1e-12, atol=1e-12)
         assert np.allclose(q_yz.numpy(), u.sum(axis=(0, 1)), rtol=1e-12, atol=1e-12)
         assert abs(stats[0].item() / stats[1].item() - rp.mean_abs_div(ref, m)) < 1e-13
+        # the pipeline's form: halos posted from the boundary planes alone, ONE all-reduce over the flat
+        # accumulator [sum|div|, n_fluid | Q_xy (own planes, zeros elsewhere) | Q_xz | Q_yz]
+        pend = comm.post_halos(wt[0], wt[-1], mt[0])
+        wb2, wa2, ma2 = comm.wait_halos(pend)
+        for a2, b2 in ((wb2, w_below), (wa2, w_above), (ma2, m_above)):
+            assert (a2 is None and b2 is None) or torch.equal(a2, b2)
+        ny, nx = shape[1], shape[2]
+        acc = torch.zeros(2 + nz + ny + nx, dtype=torch.float64)
+        acc[0] = float(np.abs(d[m[z0:z1]]).sum())
+        acc[1] = float(m[z0:z1].sum())
+        acc[2 + z0:2 + z1] = torch.from_numpy(w[z0:z1].sum(axis=(1, 2)))
+        acc[2 + nz:2 + nz + ny] = torch.from_numpy(v[z0:z1].sum(axis=(0, 2)))
+        acc[2 + nz + ny:] = torch.from_numpy(u[z0:z1].sum(axis=(0, 1)))
+        comm.reduce_profiles_(acc)
+        assert np.allclose(acc[2:2 + nz].numpy(), w.sum(axis=(1, 2)), rtol=1e-13, atol=1e-13)
+        assert np.allclose(acc[2 + nz:2 + nz + ny].numpy(), v.sum(axis=(0, 2)), rtol=1e-12, atol=1e-12)
+        assert np.allclose(acc[2 + nz + ny:].numpy(), u.sum(axis=(0, 1)), rtol=1e-12, atol=1e-12)
+        assert abs(acc[0].item() / acc[1].item() - rp.mean_abs_div(ref, m)) < 1e-13
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

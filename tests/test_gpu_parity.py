@@ -558,6 +558,43 @@ def test_c4_headline_config_sampled_voxels_vs_oracle():
     assert torch.equal(part, out[:, z0:z1])
 
 
+def test_slab_hash_matches_full_hash_and_detects_short_halos():
+    """a rank that bins only its slab's particles plus a halo gets the same neighbours as with
+    the whole cloud, and a halo that is too short is detected (the caller then redoes the frame)."""
+    dev = torch.device("cuda", 0)
+    n = 96
+    mask = synthetic.fcc_sphere_pack_mask(n, lattice=32.0, device=dev)
+    pts = synthetic.sample_pore_particles(mask, 60000, seed=9)
+    vals = synthetic.sphere_pack_flow(pts, n)
+    ax = torch.linspace(0, n - 1, n, dtype=torch.float64, device=dev)
+    m8 = mask.view(torch.uint8)
+    eng = PTVEngine(dev)
+    for method, k in (("idw", 50), ("sibson", 30), ("idw", 5)):
+        eng.build(pts, vals)
+        for z0, z1 in ((0, 24), (40, 64), (72, 96)):
+            eng.build(pts, vals)
+            full, fd, fi = eng.interpolate(ax, ax, ax[z0:z1], mask=m8[z0:z1], method=method, k=k,
+                                           out_dtype=torch.float64, return_knn=True)
+            assert eng.clip_violations() == 0
+            eng.build_slab(pts, vals, float(ax[z0]), float(ax[z1 - 1]), k)
+            info = eng.hash_info()
+            assert info["dims"][2] < 0.8 * (n / info["cell"])  # fewer cell layers than the whole cloud
+            part, pd_, pi = eng.interpolate(ax, ax, ax[z0:z1], mask=m8[z0:z1], method=method, k=k,
+                                            out_dtype=torch.float64, return_knn=True)
+            assert eng.clip_violations() == 0
+            assert torch.equal(pi, fi) and torch.equal(torch.nan_to_num(pd_, nan=-1.0), torch.nan_to_num(fd, nan=-1.0))
+            assert torch.allclose(part, full, rtol=0, atol=1e-11)
+    # a halo of a fifth of the expected neighbour radius is too short: searches leave the binned range
+    eng.build_slab(pts, vals, float(ax[40]), float(ax[63]), 50, halo_factor=0.2)
+    eng.interpolate(ax, ax, ax[40:64], mask=m8[40:64], method="idw", k=50)
+    assert eng.clip_violations() > 0
+    with pytest.raises(ValueError, match="linear"):
+        eng.interpolate(ax, ax, ax[40:64], mask=m8[40:64], method="linear")
+    eng.build(pts, vals)  # a full build clears the clipping
+    eng.interpolate(ax, ax, ax[40:64], mask=m8[40:64], method="idw", k=50)
+    assert eng.clip_violations() == 0
+
+
 def test_production_kernel_neighbour_rows_bitexact_c1_scale():
     """Neighbour rows and distances of the PRODUCTION streaming kernel (not the heap kernel) at config-1
     density: 64^3 hex pack, 12.5k vectors, k = 50 and sibson k = 30, against the canonical cKDTree lists."""
