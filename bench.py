@@ -353,6 +353,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the b200 arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from ptv_interpolation_b200 import hostmem
+    numa = hostmem.bind_host_to_device(local)  # node-local pinned buffers for the host<->device copies
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.load()
@@ -479,7 +481,7 @@ def run_b200(args):
         torch.cuda.empty_cache()
 
         def plugin_call(mask):
-            U, V, W = gi.interpolate_field(df, slab_grid, mask=mask, device=dev, **kw)
+            U, V, W = gi.interpolate_field(df, slab_grid, mask=mask, device=dev, shard_inputs=world > 1, **kw)
             return float(W[0, 0, 0])  # the result is host memory the caller can read
 
         plugin_call(mask_bool)  # first call allocates the pinned pools
@@ -495,13 +497,23 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_ms = float(t2.item()) / n_e2e
-        h2d = npart * 48 + mask_slab_np.size + 3 * n * 8
+        h2d = -(-npart // world) * 48 + mask_slab_np.size + 3 * n * 8
         d2h = 3 * nzl * n * n * 4
         e2e = {"value": total_pore / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                "via": "interpolator.interpolate_field(df, grid, method=%r, mask=mask)" % method,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timer": "wall clock, max over ranks",
                "note": "per-rank bytes; pandas DataFrame + NumPy mask in pageable host memory -> NumPy U,V,W; every rank "
-                       "stages the particle table itself and returns its own z-slab"}
+                       "uploads 1/N of the particle table (all-gathered over NVLink) and its own mask slab and "
+                       "returns its own z-slab",
+               "host_numa_binding": numa}
+        sink = os.path.join(ROOT, "profiles", f"r02_host_sink_n{world}.json")
+        if os.path.exists(sink):  # measured floor: all ranks draining their slabs into pinned host memory at once
+            try:
+                floor_ms = 1e3 * json.load(open(sink))["d2h_sink"]["best_s"]
+                e2e["host_sink_floor_ms"] = floor_ms
+                e2e["frac_of_host_sink"] = floor_ms / e2e_ms
+            except Exception:
+                pass
         # the unmodified reference call (main.py:184-192 passes no mask): every voxel is interpolated
         if not args.no_all_voxel:
             barrier()

@@ -96,6 +96,9 @@ int ptv_hash_destroy(ptv_hash* h);
 int ptv_hash_build_slab(ptv_hash* h, const double* d_points, const double* d_values, int64_t n, double cell_size,
                         double z_lo, double z_hi, int k, double halo_factor, void* stream);
 int ptv_hash_clip_violations(const ptv_hash* h, int64_t* count);
+/* The same count written to a device double on the stream (no synchronisation): lets the caller fold it into
+ * the all-reduce of the flux / divergence statistics and decide about the fall-back collectively. */
+int ptv_hash_clip_violations_to(const ptv_hash* h, double* d_dst, void* stream);
 int ptv_hash_build(ptv_hash* h, const double* d_points, const double* d_values, int64_t n,
                    double cell_size, void* stream);
 int ptv_hash_info(const ptv_hash* h, int64_t* n, int dims[3], double origin[3], double* cell_size,

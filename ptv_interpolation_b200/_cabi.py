@@ -23,7 +23,7 @@ _lib = None
 
 EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
-    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_build_slab", "ptv_hash_clip_violations", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_work_stats", "ptv_linear_stats", "ptv_knn_points", "ptv_outlier_filter",
+    "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_build_slab", "ptv_hash_clip_violations", "ptv_hash_clip_violations_to", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_work_stats", "ptv_linear_stats", "ptv_knn_points", "ptv_outlier_filter",
     "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_strain_vorticity", "ptv_poisson_workspace_bytes", "ptv_poisson_lsqr", "ptv_projection_correct",
     "ptv_interpolate_host",
@@ -58,6 +58,8 @@ def _declare(lib):
     lib.ptv_hash_build_slab.argtypes = [vp, vp, vp, i64, f64, f64, f64, i32, f64, vp]
     lib.ptv_hash_clip_violations.restype = i32
     lib.ptv_hash_clip_violations.argtypes = [vp, C.POINTER(i64)]
+    lib.ptv_hash_clip_violations_to.restype = i32
+    lib.ptv_hash_clip_violations_to.argtypes = [vp, vp, vp]
     lib.ptv_hash_info.restype = i32
     lib.ptv_hash_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32 * 3), C.POINTER(f64 * 3), C.POINTER(f64),
                                   C.POINTER(i32)]

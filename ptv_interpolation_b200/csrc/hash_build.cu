@@ -421,6 +421,16 @@ extern "C" int ptv_hash_clip_violations(const ptv_hash* h, int64_t* count) {
   return PTV_OK;
 }
 
+__global__ void clip_to_double_kernel(const int* __restrict__ count, double* __restrict__ dst) { *dst = (double)*count; }
+
+extern "C" int ptv_hash_clip_violations_to(const ptv_hash* h, double* d_dst, void* stream_) {
+  if (!h || !d_dst || h->clip_count == nullptr) { set_error("ptv_hash_clip_violations_to: NULL argument / hash not built"); return PTV_ERR_INVALID; }
+  clip_to_double_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(h->clip_count, d_dst);
+  count_launches(1);
+  PTV_CUDA(cudaGetLastError());
+  return PTV_OK;
+}
+
 static int build_impl(ptv_hash* h, const double* d_points, const double* d_values, int64_t n, double cell_size,
                       bool slab, double z_lo, double z_hi, int k, double halo_factor, void* stream_) {
   if (!h || !d_points || !d_values) { set_error("ptv_hash_build: NULL argument"); return PTV_ERR_INVALID; }

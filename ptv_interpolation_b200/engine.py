@@ -121,6 +121,11 @@ class PTVEngine:
             _cabi.check(self.lib.ptv_hash_clip_violations(self._h, C.byref(c)))
         return int(c.value)
 
+    def clip_violations_to(self, dst: torch.Tensor):
+        """clip_violations() written into a one-element float64 CUDA tensor on the current stream (no sync)."""
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ptv_hash_clip_violations_to(self._h, _ptr(dst), self._stream()))
+
     def hash_info(self):
         n = C.c_int64()
         dims = (C.c_int * 3)()
@@ -342,11 +347,11 @@ class PTVEngine:
         return (div, stats) if with_stats else div
 
     def divergence_flux(self, u, v, w, mask, dx, dy, dz, w_below=None, w_above=None, mask_above=None, z0=0,
-                        nz_global=None):
+                        nz_global=None, extra=0):
         """One pass: (div, stats[2] = (sum|div| over fluid, n_fluid), q_xy[nz], q_xz[ny], q_yz[nx]).
         With ``nz_global`` the accumulators live in one flat buffer laid out for the whole grid -- Q_xy of
         this slab at planes z0.. -- so that a single all-reduce finishes all of them (returned as the sixth
-        value; q_xy is then the full-length profile)."""
+        value; q_xy is then the full-length profile; ``extra`` more zeroed slots follow Q_yz for the caller)."""
         nz, ny, nx = u.shape
         if mask.dtype == torch.bool:
             mask = mask.view(torch.uint8)
@@ -355,8 +360,9 @@ class PTVEngine:
         u, v, w, mask = u.contiguous(), v.contiguous(), w.contiguous(), mask.contiguous()
         div = torch.empty_like(u)
         nzg = nz if nz_global is None else int(nz_global)
-        acc = torch.zeros(2 + nzg + ny + nx, dtype=torch.float64, device=self.device)
-        stats, qxy, qxz, qyz = acc[:2], acc[2:2 + nzg], acc[2 + nzg:2 + nzg + ny], acc[2 + nzg + ny:]
+        acc = torch.zeros(2 + nzg + ny + nx + extra, dtype=torch.float64, device=self.device)
+        stats, qxy, qxz, qyz = (acc[:2], acc[2:2 + nzg], acc[2 + nzg:2 + nzg + ny],
+                                acc[2 + nzg + ny:2 + nzg + ny + nx])
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.ptv_divergence_flux(_ptr(u), _ptr(v), _ptr(w), _ptr(mask), nx, ny, nz, float(dx),
                                                      float(dy), float(dz), _ptr(w_below), _ptr(w_above),

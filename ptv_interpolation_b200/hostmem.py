@@ -4,7 +4,7 @@
 functions need are kept and reused:
 
 * ``stage_to_device``: pageable NumPy array -> cached pinned staging chunk(s) -> device tensor.  The host
-  copy into the pinned chunk runs on torch's CPU thread pool and overlaps the DMA of the previous chunk
+  copy into the pinned chunk is split over a few threads and overlaps the DMA of the previous chunk
   (two chunks in flight).
 * ``ResultPool``: pinned result buffers keyed by (shape, dtype).  A buffer is handed out as a NumPy array;
   it returns to the pool when the caller has dropped every view of it (weakref finaliser), so results a
@@ -12,6 +12,7 @@ functions need are kept and reused:
 """
 from __future__ import annotations
 
+import os
 import threading
 import warnings
 import weakref
@@ -21,6 +22,30 @@ import torch
 
 _CHUNK_BYTES = 64 << 20
 _lock = threading.Lock()
+_pool = None
+
+
+def _copy_pool():
+    """A few host threads for the pageable -> pinned copies (np.copyto releases the GIL).  Independent of
+    OMP_NUM_THREADS, which torchrun pins to 1; sized so that the ranks of one node share the cores."""
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        _pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1) // ranks)))
+    return _pool
+
+
+def _parallel_copy(dst, src):
+    """dst[:] = src for two 1-D uint8 NumPy arrays, split over the copy threads."""
+    n = dst.shape[0]
+    pool = _copy_pool()
+    parts = pool._max_workers
+    if parts == 1 or n < (4 << 20):
+        np.copyto(dst, src)
+        return
+    step = -(-n // parts)
+    list(pool.map(lambda a: np.copyto(dst[a:a + step], src[a:a + step]), range(0, n, step)))
 _staging = {}  # device index -> [pinned uint8 tensor, pinned uint8 tensor, events]
 
 
@@ -39,11 +64,8 @@ def stage_to_device(arr, dev, out=None, stream=None):
     the pinned staging chunks; the DMAs run on ``stream`` (default: the current stream).  Returns when the
     host array has been fully read and the last DMA has completed."""
     arr = np.ascontiguousarray(arr)
-    with warnings.catch_warnings():  # read-only inputs (broadcast views, memory maps) are only read here
-        warnings.simplefilter("ignore", UserWarning)
-        t_host = torch.from_numpy(arr.view(np.uint8).reshape(-1)) if arr.dtype == np.bool_ else \
-            torch.from_numpy(arr.reshape(-1).view(np.uint8))
-    nbytes = t_host.numel()
+    h_flat = arr.view(np.uint8).reshape(-1) if arr.dtype == np.bool_ else arr.reshape(-1).view(np.uint8)
+    nbytes = h_flat.shape[0]
     tdt = torch.from_numpy(np.empty(0, dtype=np.uint8 if arr.dtype == np.bool_ else arr.dtype)).dtype
     if out is None:
         out = torch.empty(arr.shape, dtype=tdt, device=dev)
@@ -59,7 +81,7 @@ def stage_to_device(arr, dev, out=None, stream=None):
         n = min(_CHUNK_BYTES, nbytes - off)
         if used[b]:
             evs[b].synchronize()  # the DMA that last read this chunk has finished
-        bufs[b][:n].copy_(t_host[off:off + n])  # host -> pinned (torch's CPU thread pool)
+        _parallel_copy(bufs[b].numpy()[:n], h_flat[off:off + n])  # host -> pinned, a few threads
         with torch.cuda.stream(stream):
             dflat[off:off + n].copy_(bufs[b][:n], non_blocking=True)
         evs[b].record(stream)
@@ -68,6 +90,40 @@ def stage_to_device(arr, dev, out=None, stream=None):
         if used[b]:
             evs[b].synchronize()
     return out
+
+
+def bind_host_to_device(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs ``local_cpulist`` of its PCI
+    device), so that the pinned buffers allocated afterwards are node-local and host<->device DMA does not
+    cross the socket interconnect.  One process per GPU; call before the first pinned allocation.  Returns a
+    dict describing what was done ({} if the topology cannot be read -- then nothing changes)."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        with open(base + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return {"pci": bus, "cpus": len(allowed), "changed": False}
+        os.sched_setaffinity(0, cpus)
+        node = None
+        try:
+            with open(base + "/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
+        return {"pci": bus, "numa_node": node, "cpus": len(cpus), "changed": True}
+    except Exception:
+        return {}
 
 
 class ResultPool:

@@ -95,9 +95,12 @@ def _grid_axes(grid_tuple):
 
 def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_kernel="thin_plate_spline",
                       smoothing=0.0, n_jobs=1, idw_power=2.0, idw_neighbors=50, sibson_neighbors=30,
-                      mask=None, out_dtype=np.float32, device=None, return_knn=False):
+                      mask=None, out_dtype=np.float32, device=None, return_knn=False, shard_inputs=False):
     """interpolator.py:65-203.  ``n_jobs`` is accepted and ignored (one GPU does the work).
-    Returns (U, V, W): three writable (nz, ny, nx) views of one host array, like the reference."""
+    Returns (U, V, W): three writable (nz, ny, nx) views of one host array, like the reference.
+    ``shard_inputs=True`` (one process per GPU under torch.distributed, every rank calling with the SAME
+    DataFrame and its own z-slab of the grid): each rank uploads 1/N of the particle table and the ranks
+    all-gather it over NVLink instead of N full host->device copies."""
     import torch
     if method not in _GPU_METHODS:
         # interpolator.py:197 hands every other name to griddata, which knows 'cubic' only in 1-D / 2-D
@@ -118,8 +121,8 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     # particle table (interpolator.py:78-79): the six columns go to the device one by one through the pinned
     # staging chunks and are interleaved into (Np,3) rows THERE -- df[[...]].values would transpose 2 x 24 B
     # per particle on one host core first
-    pts = _columns_to_device(df, ("x", "y", "z"), dev)
-    vals = _columns_to_device(df, ("u", "v", "w"), dev)
+    pts = _columns_to_device(df, ("x", "y", "z"), dev, shard_inputs)
+    vals = _columns_to_device(df, ("u", "v", "w"), dev, shard_inputs)
     npart = pts.shape[0]
     k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors, "linear": 4}[method]
     if method == "rbf":
@@ -160,14 +163,31 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
 _dev_results = {}
 
 
-def _columns_to_device(df, cols, dev):
-    """(Np, len(cols)) float64 device tensor of the DataFrame's columns, rows interleaved on the device."""
+def _columns_to_device(df, cols, dev, shard=False):
+    """(Np, len(cols)) float64 device tensor of the DataFrame's columns, rows interleaved on the device.
+    ``shard``: this rank uploads only its 1/N of the rows, the ranks all-gather the rest over NCCL."""
     import torch
+    import torch.distributed as dist
     from . import hostmem
-    out = torch.empty((len(df), len(cols)), dtype=torch.float64, device=dev)
+    n = len(df)
+    out = torch.empty((n, len(cols)), dtype=torch.float64, device=dev)
+    world = dist.get_world_size() if (shard and dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        for j, c in enumerate(cols):
+            col = np.ascontiguousarray(df[c].to_numpy(dtype=np.float64, copy=False))
+            out[:, j] = hostmem.stage_to_device(col, dev)
+        return out
+    rank = dist.get_rank()
+    m = -(-n // world)  # rows per rank, the last shard is padded
+    lo, hi = min(rank * m, n), min((rank + 1) * m, n)
+    mine = torch.zeros((len(cols), m), dtype=torch.float64, device=dev)
     for j, c in enumerate(cols):
-        col = np.ascontiguousarray(df[c].to_numpy(dtype=np.float64, copy=False))
-        out[:, j] = hostmem.stage_to_device(col, dev)
+        col = np.ascontiguousarray(df[c].to_numpy(dtype=np.float64, copy=False)[lo:hi])
+        if hi > lo:
+            hostmem.stage_to_device(col, dev, out=mine[j, :hi - lo])
+    gathered = torch.empty((world, len(cols), m), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(gathered, mine)
+    out.copy_(gathered.permute(0, 2, 1).reshape(world * m, len(cols))[:n])
     return out
 
 

@@ -61,15 +61,15 @@ def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, c
     dx, dy, dz = spacing
     div, stats, q_xy, q_xz, q_yz, acc = eng.divergence_flux(uvw[0], uvw[1], uvw[2], mask_slab, dx, dy, dz,
                                                             w_below=w_below, w_above=w_above, mask_above=m_above,
-                                                            z0=comm.z0, nz_global=comm.nz)
-    comm.reduce_profiles_(acc)  # one all-reduce: (sum|div|, n_fluid), Q_xy, Q_xz, Q_yz
+                                                            z0=comm.z0, nz_global=comm.nz, extra=1)
+    if slab_hash:
+        eng.clip_violations_to(acc[-1:])  # rides along in the all-reduce below
+    comm.reduce_profiles_(acc)  # one all-reduce: (sum|div|, n_fluid), Q_xy, Q_xz, Q_yz (+ halo violations)
     if slab_hash:
         # exact fall-back: some voxel's k-th neighbour may lie beyond the halo -> redo the frame on the full
-        # hash, on every rank (the decision is collective so that the halo exchange stays matched)
-        viol = torch.tensor([eng.clip_violations()], dtype=torch.int64, device=eng.device)
-        if comm.on:
-            torch.distributed.all_reduce(viol, op=torch.distributed.ReduceOp.MAX, group=comm.group)
-        if int(viol.item()) > 0:
+        # hash, on every rank (the sum is the same everywhere, so the decision is collective and the halo
+        # exchange stays matched)
+        if float(acc[-1].item()) > 0.0:
             eng.build(points, values)
             return hot_path_step(eng, points, values, ax_x, ax_y, ax_z, mask_slab, comm, method=method, k=k,
                                  idw_power=idw_power, spacing=spacing, out=uvw, out_dtype=out_dtype, rebuild=False)

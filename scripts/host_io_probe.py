@@ -27,17 +27,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--bind", action="store_true", help="pin every rank to the CPUs next to its GPU first")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = {}
+    if a.bind:
+        from ptv_interpolation_b200 import hostmem
+        numa = hostmem.bind_host_to_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = a.n
     nzl = n // world
-    res = {"world": world, "grid": n}
+    res = {"world": world, "grid": n, "numa_binding_rank0": numa}
 
     def barrier():
         torch.cuda.synchronize()
