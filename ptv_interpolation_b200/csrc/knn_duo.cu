@@ -30,7 +30,7 @@ namespace ptv {
 
 static constexpr int kDNB = 64;    // histogram bins over [0, Tmax)
 static constexpr int kDList = 16;  // crossing-bin list capacity per voxel
-static constexpr int kDCH = 64;    // records per staged chunk
+static constexpr int kDCH = 32;    // records per staged chunk; two chunks are resident (one in flight)
 static constexpr int kDW = 4;      // warps per CTA
 static constexpr int kDT = kDW * 32;
 static constexpr int kDVPT = 16;   // voxels of the region per thread (region = 8 x 8 x 32)
@@ -47,13 +47,15 @@ struct __align__(16) WarpScan {  // iterator over the cell list around the warp'
   double R, R2, pR2;             // current / previous scan radius
   int y0, y1, z0, z1;            // rows of the current region (cell coordinates)
   int py0, py1, pz0, pz1;        // rows of the previous one (shell scans)
-  int have_prev, nslots, sb, c0, total, pad;
+  int have_prev, nslots, sb, c0, total;
+  int pend_m, pend_half, cur_off;  // records / half of the chunk in flight; offset (0 / kDCH) of the current chunk
+  int pad0, pad1;
 };
 static constexpr size_t kColBytes = (size_t)kDNB * 32 * 2 * sizeof(uint16_t);  // 8 KB: [bin][lane][voxel]
 static_assert(kColBytes >= (size_t)2 * kDList * 32 * 8, "lists must fit under the histograms");
 static constexpr size_t kOffS32 = kColBytes;
-static constexpr size_t kOffS64 = kOffS32 + kDCH * sizeof(float4);
-static constexpr size_t kOffVal = kOffS64 + kDCH * sizeof(ParticleRec);
+static constexpr size_t kOffS64 = kOffS32 + 2 * kDCH * sizeof(float4);
+static constexpr size_t kOffVal = kOffS64 + 2 * kDCH * sizeof(ParticleRec);
 template <typename OutT> struct DuoVal;
 template <> struct DuoVal<float> {
   using type = float4;
@@ -71,14 +73,15 @@ template <> struct DuoVal<double> {
 };
 template <typename OutT> struct WarpLayout {
   using ValT = typename DuoVal<OutT>::type;
-  static constexpr size_t kOffSeg = kOffVal + kDCH * sizeof(ValT);
-  static constexpr size_t kOffScan = kOffSeg + 72 * sizeof(int);
+  static constexpr size_t kOffSeg = kOffVal + 2 * kDCH * sizeof(ValT);
+  static constexpr size_t kOffScan = kOffSeg + (72 + 2 * kDCH) * sizeof(int);
   static constexpr size_t kBytes = kOffScan + sizeof(WarpScan);
   __device__ static float4* s32(unsigned char* wb) { return reinterpret_cast<float4*>(wb + kOffS32); }
   __device__ static ParticleRec* s64(unsigned char* wb) { return reinterpret_cast<ParticleRec*>(wb + kOffS64); }
   __device__ static ValT* sval(unsigned char* wb) { return reinterpret_cast<ValT*>(wb + kOffVal); }
   __device__ static int* seg_start(unsigned char* wb) { return reinterpret_cast<int*>(wb + kOffSeg); }
   __device__ static int* seg_off(unsigned char* wb) { return reinterpret_cast<int*>(wb + kOffSeg) + 32; }
+  __device__ static int* spos(unsigned char* wb) { return reinterpret_cast<int*>(wb + kOffSeg) + 72; }  // [2 * kDCH]
   __device__ static WarpScan* scan(unsigned char* wb) { return reinterpret_cast<WarpScan*>(wb + kOffScan); }
 };
 
@@ -134,6 +137,7 @@ __device__ __noinline__ void duo_begin_scan(const HashGrid* gs, WarpScan* sc, do
     sc->sb = 0;
     sc->c0 = 0;
     sc->total = 0;
+    sc->pend_m = 0;
   }
   __syncwarp();
 }
@@ -147,6 +151,7 @@ __device__ __forceinline__ void duo_restart_scan(WarpScan* sc) {
     sc->sb = 0;
     sc->c0 = 0;
     sc->total = 0;
+    sc->pend_m = 0;
   }
   __syncwarp();
 }
@@ -198,63 +203,95 @@ __device__ __forceinline__ void duo_resolve_slot(const HashGrid& g, const WarpSc
   }
 }
 
-// Stage the next chunk of up to kDCH records of the scan into the warp's buffers and return its size
-// (0 = the scan is over).  float32 entries are centre-relative x, y, z and |c|^2, padded with far-away
-// sentinels up to the next multiple of 32; with_exact also stages the 32-byte records and the values.
+__device__ __forceinline__ void duo_cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// Start the asynchronous copies (LDGSTS, no registers) of the records [c0, c0 + m) of the current slot batch
+// into buffer half `half`: 32-byte records, their values (with_exact), and the sorted position of each.
+template <typename OutT>
+__device__ __forceinline__ void duo_issue_chunk(const HashGrid& g, unsigned char* wb, int c0, int m, int half,
+                                                int with_exact) {
+  using L = WarpLayout<OutT>;
+  const int lane = threadIdx.x & 31;
+  if (lane < m) {
+    const int* seg_start = L::seg_start(wb);
+    const int* seg_off = L::seg_off(wb);
+    const int gpos = c0 + lane;
+    int lo = 0, hi2 = 31;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {  // record gpos lives in the last segment whose offset <= gpos
+      const int mid = (lo + hi2 + 1) >> 1;
+      if (seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
+    }
+    const int spos = seg_start[lo] + (gpos - seg_off[lo]);
+    const int j = half * kDCH + lane;
+    const char* src = reinterpret_cast<const char*>(g.rec + spos);
+    char* dst = reinterpret_cast<char*>(L::s64(wb) + j);
+    duo_cp_async16(dst, src);
+    duo_cp_async16(dst + 16, src + 16);
+    if (with_exact) {
+      if (sizeof(OutT) == 4) {
+        duo_cp_async16(L::sval(wb) + j, g.vals_s32 + spos);
+      } else {
+        const char* vs = reinterpret_cast<const char*>(g.vals_s64 + spos);
+        char* vd = reinterpret_cast<char*>(L::sval(wb) + j);
+        duo_cp_async16(vd, vs);
+        duo_cp_async16(vd + 16, vs + 16);
+      }
+    }
+    L::spos(wb)[j] = spos;
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+// Hand the next chunk of up to kDCH records of the scan to the caller and return its size (0 = the scan is
+// over); the chunk sits at offset sc->cur_off of the staging arrays.  float32 entries are centre-relative
+// x, y, z and |c|^2, padded with far-away sentinels up to kDCH; with_exact also stages the values.  While the
+// caller works on this chunk the next one of the slot batch is already travelling global -> shared
+// (cp.async into the other buffer half), so the staging latency is paid once per batch, not per chunk.
 // Only __syncwarp(): the warps of a CTA never wait for each other.
 template <typename OutT>
 __device__ __noinline__ int duo_next_chunk(const HashGrid* gs, unsigned char* wb, int with_exact) {
   using L = WarpLayout<OutT>;
   const HashGrid& g = *gs;
   WarpScan* sc = L::scan(wb);
-  int* seg_start = L::seg_start(wb);
-  int* seg_off = L::seg_off(wb);
   const int lane = threadIdx.x & 31;
   __syncwarp();  // the previous chunk has been consumed by every lane
   for (;;) {
-    const int c0 = sc->c0, total = sc->total;
-    if (c0 < total) {
-      const int m = min(kDCH, total - c0);
-      const int mpad = (m + 31) & ~31;
-      const double cx = sc->cx, cy = sc->cy, cz = sc->cz;
+    const int pend_m = sc->pend_m, half = sc->pend_half, c0 = sc->c0, total = sc->total;
+    if (pend_m > 0) {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // this lane's copies have landed
+      const int j = half * kDCH + lane;
       float4* s32 = L::s32(wb);
-#pragma unroll
-      for (int h = 0; h < kDCH / 32; ++h) {
-        const int j = lane + 32 * h;
-        if (j < m) {
-          const int gpos = c0 + j;
-          int lo = 0, hi2 = 31;
-#pragma unroll
-          for (int it = 0; it < 5; ++it) {  // record gpos lives in the last segment whose offset <= gpos
-            const int mid = (lo + hi2 + 1) >> 1;
-            if (seg_off[mid] <= gpos) lo = mid; else hi2 = mid - 1;
-          }
-          const int spos = seg_start[lo] + (gpos - seg_off[lo]);
-          const int4* src = reinterpret_cast<const int4*>(g.rec + spos);
-          const int4 a = __ldg(src);
-          const int4 c = __ldg(src + 1);
-          const double px = __hiloint2double(a.y, a.x), py = __hiloint2double(a.w, a.z);
-          const double pz = __hiloint2double(c.y, c.x);
-          const float fx = (float)(px - cx), fy = (float)(py - cy), fz = (float)(pz - cz);
-          s32[j] = make_float4(fx, fy, fz, fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
-          if (with_exact) {
-            int4* dst = reinterpret_cast<int4*>(L::s64(wb) + j);
-            dst[0] = a;
-            dst[1] = make_int4(c.x, c.y, c.z, spos);  // pad word: the record's cell-sorted position
-            L::sval(wb)[j] = DuoVal<OutT>::load(g, spos);
-          }
-        } else if (j < mpad) {
-          s32[j] = make_float4(0.0f, 0.0f, 0.0f, INFINITY);  // never accepted, lands in the last bin
-        }
+      if (lane < pend_m) {
+        int4* recp = reinterpret_cast<int4*>(L::s64(wb) + j);
+        const int4 a = recp[0];
+        const int4 c = recp[1];
+        const double px = __hiloint2double(a.y, a.x), py = __hiloint2double(a.w, a.z);
+        const double pz = __hiloint2double(c.y, c.x);
+        const float fx = (float)(px - sc->cx), fy = (float)(py - sc->cy), fz = (float)(pz - sc->cz);
+        s32[j] = make_float4(fx, fy, fz, fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
+        reinterpret_cast<int*>(recp)[7] = L::spos(wb)[j];  // pad word: the record's cell-sorted position
+      } else {
+        s32[j] = make_float4(0.0f, 0.0f, 0.0f, INFINITY);  // never accepted, lands in the last bin
+      }
+      const int mnext = min(kDCH, total - c0);
+      if (mnext > 0) duo_issue_chunk<OutT>(g, wb, c0, mnext, half ^ 1, with_exact);
+      __syncwarp();
+      if (lane == 0) {
+        sc->cur_off = half * kDCH;
+        sc->pend_m = mnext > 0 ? mnext : 0;
+        sc->pend_half = half ^ 1;
+        sc->c0 = c0 + (mnext > 0 ? kDCH : 0);
       }
       __syncwarp();
-      if (lane == 0) sc->c0 = c0 + kDCH;
-      __syncwarp();
-      return m;
+      return pend_m;
     }
     const int sb = sc->sb, nslots = sc->nslots;
     if (sb >= nslots) return 0;
-    // next batch of 32 row slots -> record ranges, prefix offsets
+    // next batch of 32 row slots -> record ranges, prefix offsets; its first chunk starts travelling at once
     int start, cnt;
     duo_resolve_slot(g, sc, sb + lane, nslots, start, cnt);
     int inc = cnt;
@@ -264,13 +301,20 @@ __device__ __noinline__ int duo_next_chunk(const HashGrid* gs, unsigned char* wb
       if (lane >= o) inc += x;
     }
     const int tot = __shfl_sync(kFull, inc, 31);
-    seg_start[lane] = start;
-    seg_off[lane] = inc - cnt;
-    if (lane == 31) seg_off[32] = tot;
+    L::seg_start(wb)[lane] = start;
+    L::seg_off(wb)[lane] = inc - cnt;
+    if (lane == 31) L::seg_off(wb)[32] = tot;
+    __syncwarp();
+    const int m0 = min(kDCH, tot);
+    const int h0 = (sc->cur_off / kDCH) ^ 1;  // not the half the caller may still be reading
+    if (m0 > 0) duo_issue_chunk<OutT>(g, wb, 0, m0, h0, with_exact);
+    __syncwarp();
     if (lane == 0) {
       sc->sb = sb + 32;
-      sc->c0 = 0;
       sc->total = tot;
+      sc->c0 = m0 > 0 ? kDCH : 0;
+      sc->pend_m = m0;
+      sc->pend_half = h0;
     }
     __syncwarp();
   }
@@ -500,8 +544,8 @@ __device__ __noinline__ void duo_subbin_pass(const HashGrid* gs, unsigned char* 
   for (;;) {
     const int m = duo_next_chunk<OutT>(gs, wb, 0);
     if (m == 0) break;
-    const int mpad = (m + 31) & ~31;
-    for (int j = 0; j < mpad; ++j) {
+    const int off = L::scan(wb)->cur_off;
+    for (int j = off; j < off + kDCH; ++j) {
       const float4 c = s32[j];
       const float f0 = fmaf(ax0, c.x, fmaf(ay0, c.y, fmaf(az0, c.z, fmaf(c.w, inv_w, b0))));
       const float f1 = fmaf(ax1, c.x, fmaf(ay1, c.y, fmaf(az1, c.z, fmaf(c.w, inv_w, b1))));
@@ -689,6 +733,8 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
         sc->cz = 0.5 * (v6[2] - v6[5]);
         sc->rmax = sqrt(r2) * (1.0 + 1e-9) + 1e-3 * g.cell;
         sc->R2 = 0.0;
+        sc->cur_off = 0;
+        sc->pend_m = 0;
       }
       __syncwarp();
     }
@@ -738,9 +784,9 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
           const int m = duo_next_chunk<OutT>(gs, wb, 0);
           if (m == 0) break;
           staged += m;
-          const int mpad = (m + 31) & ~31;
+          const int off = sc->cur_off;
 #pragma unroll 1
-          for (int j0 = 0; j0 < mpad; j0 += 8) {
+          for (int j0 = off; j0 < off + kDCH; j0 += 8) {
             // all loads and bin indices of eight candidates first: the counter updates below are the only
             // dependent chain left (shared-memory stores may alias the staged candidates for the compiler)
             int b0[8], b1[8];
@@ -866,9 +912,8 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
       const int m = duo_next_chunk<OutT>(gs, wb, 1);
       if (m == 0) break;
       staged_b += m;
-      const int mpad = (m + 31) & ~31;
-#pragma unroll 1
-      for (int base = 0; base < mpad; base += 32) {
+      const int base = sc->cur_off;
+      {
         unsigned mk[2] = {0u, 0u};
 #pragma unroll 1
         for (int j8 = 0; j8 < 32; j8 += 8) {  // small body: the decoupled warps share the instruction cache
@@ -1023,9 +1068,8 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
         const int m = duo_next_chunk<OutT>(gs, wb, 1);
         if (m == 0) break;
         staged_c += m;
-        const int mpad = (m + 31) & ~31;
-#pragma unroll 1
-        for (int base = 0; base < mpad; base += 32) {
+        const int base = sc->cur_off;
+        {
           unsigned mk[2] = {0u, 0u};
 #pragma unroll 1
           for (int j8 = 0; j8 < 32; j8 += 8) {
