@@ -161,6 +161,13 @@ int ptv_mask_gather(const uint8_t* d_mask_raw, int rnx, int rny, int rnz, const 
 /* ---- no-slip wall particles: replaces extract_boundary_particles (interpolator.py:240-284).
  *      Flags solid voxels within `thickness` 6-connected dilation steps of fluid, compacts
  *      their linear indices in C order into d_indices (capacity `cap`), total in *h_count. */
+/* The same with a caller-owned workspace of ptv_boundary_workspace_bytes() bytes, in two phases so that the
+ * caller can size the index array: phase 0 packs the mask into bits, dilates, flags and counts (-> *h_count,
+ * synchronises); phase 1 writes the indices from the flag words phase 0 left in the workspace.  thickness < 1
+ * behaves like binary_dilation(iterations < 1): dilate until nothing changes. */
+int64_t ptv_boundary_workspace_bytes(int nx, int ny, int nz);
+int ptv_boundary_voxels_ws(const uint8_t* d_mask, int nx, int ny, int nz, int thickness, void* d_work, int phase,
+                           int64_t* d_indices, int64_t cap, int64_t* h_count, void* stream);
 int ptv_boundary_voxels(const uint8_t* d_mask, int nx, int ny, int nz, int thickness,
                         int64_t* d_indices, int64_t cap, int64_t* h_count, void* stream);
 

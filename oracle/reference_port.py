@@ -428,7 +428,12 @@ def extract_boundary_particles(mask, bounds, sampling_step=1, thickness=1):
     nz, ny, nx = mask.shape
     (xmin, xmax), (ymin, ymax), (zmin, zmax) = bounds
     cur = np.asarray(mask, dtype=bool)
-    for _ in range(thickness):
+    steps = thickness
+    if thickness < 1:
+        # scipy.ndimage.binary_dilation(iterations < 1) repeats until nothing changes: with 6-connectivity and
+        # border_value = 0 that fills the whole box as soon as one voxel is fluid
+        steps = (nz + ny + nx) if cur.any() else 0
+    for _ in range(steps):
         nxt = cur.copy()
         nxt[1:, :, :] |= cur[:-1, :, :]
         nxt[:-1, :, :] |= cur[1:, :, :]

@@ -24,7 +24,7 @@ _lib = None
 EXPORTS = [
     "ptv_version", "ptv_last_error", "ptv_device_info", "ptv_set_tuning", "ptv_get_tuning", "ptv_launch_count",
     "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_build_slab", "ptv_hash_clip_violations", "ptv_hash_clip_violations_to", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_work_stats", "ptv_linear_stats", "ptv_knn_points", "ptv_outlier_filter",
-    "ptv_mask_gather", "ptv_boundary_voxels", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
+    "ptv_mask_gather", "ptv_boundary_voxels", "ptv_boundary_voxels_ws", "ptv_boundary_workspace_bytes", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_strain_vorticity", "ptv_poisson_workspace_bytes", "ptv_poisson_lsqr", "ptv_projection_correct",
     "ptv_interpolate_host",
 ]
@@ -81,6 +81,10 @@ def _declare(lib):
     lib.ptv_mask_gather.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
     lib.ptv_boundary_voxels.restype = i32
     lib.ptv_boundary_voxels.argtypes = [vp, i32, i32, i32, i32, vp, i64, C.POINTER(i64), vp]
+    lib.ptv_boundary_workspace_bytes.restype = i64
+    lib.ptv_boundary_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ptv_boundary_voxels_ws.restype = i32
+    lib.ptv_boundary_voxels_ws.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp, i64, C.POINTER(i64), vp]
     lib.ptv_apply_mask.restype = i32
     lib.ptv_apply_mask.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     lib.ptv_divergence.restype = i32

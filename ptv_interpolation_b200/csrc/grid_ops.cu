@@ -48,27 +48,63 @@ __global__ void __launch_bounds__(256) mask_gather_kernel(const uint8_t* __restr
 }
 
 // ------------------------------------------------------------------ boundary voxels (a3)
-// One 6-connected dilation step with border_value = 0 (scipy.ndimage.binary_dilation).
-__global__ void __launch_bounds__(256) dilate6_kernel(const uint8_t* __restrict__ in, int nx, int ny, int nz,
-                                                       uint8_t* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n = (int64_t)nx * ny * nz;
-  if (i >= n) return;
-  const int x = (int)(i % nx);
-  const int y = (int)((i / nx) % ny);
-  const int z = (int)(i / ((int64_t)nx * ny));
-  const int64_t sy = nx, sz = (int64_t)nx * ny;
-  uint8_t r = in[i] != 0;
-  if (!r) {
-    r = (x > 0 && in[i - 1]) || (x + 1 < nx && in[i + 1]) || (y > 0 && in[i - sy]) ||
-        (y + 1 < ny && in[i + sy]) || (z > 0 && in[i - sz]) || (z + 1 < nz && in[i + sz]);
+// Solid voxels within `thickness` 6-connected dilation steps of fluid (scipy.ndimage.binary_dilation with
+// border_value = 0, interpolator.py:256-262), as an ordered index list.  Everything runs on a BIT-PACKED copy
+// of the mask (32 voxels of one x-row per word, rows padded to whole words): packing reads the byte mask
+// once, a dilation step is seven word reads and one word write per 32 voxels, the flags are
+// dilated & ~mask on words, and the ordered compaction walks set bits.
+__global__ void __launch_bounds__(256) pack_mask_kernel(const uint8_t* __restrict__ mask, int nx, int wx, int64_t nrows,
+                                                         uint32_t* __restrict__ bits, int* __restrict__ any_fluid) {
+  const int64_t wid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (wid >= nrows * wx) return;
+  const int64_t row = wid / wx;
+  const int xw = (int)(wid % wx);
+  const uint8_t* src = mask + row * nx + (int64_t)xw * 32;
+  const int valid = min(32, nx - xw * 32);
+  uint32_t w = 0u;
+  if (valid == 32 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {  // four mask bytes -> four bits (multiply gathers the 0/1 bytes into a nibble)
+      const uint32_t b = __vcmpne4(reinterpret_cast<const uint32_t*>(src)[q], 0u) & 0x01010101u;
+      w |= ((b * 0x01020408u) >> 24 & 0xfu) << (4 * q);
+    }
+  } else {
+    for (int j = 0; j < valid; ++j) w |= (src[j] != 0 ? 1u : 0u) << j;
   }
-  out[i] = r;
+  bits[wid] = w;
+  if (w != 0u && *any_fluid == 0) *any_fluid = 1;
+}
+
+// One 6-connected dilation step on the packed volume; `fill` != 0: every voxel becomes set if the input has
+// any set voxel at all (binary_dilation with iterations < 1 repeats until nothing changes).
+__global__ void __launch_bounds__(256) dilate_bits_kernel(const uint32_t* __restrict__ in, int nx, int wx, int ny, int nz,
+                                                           uint32_t* __restrict__ out, const int* __restrict__ fill) {
+  const int64_t wid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nwords = (int64_t)wx * ny * nz;
+  if (wid >= nwords) return;
+  const int xw = (int)(wid % wx);
+  const int y = (int)((wid / wx) % ny);
+  const int z = (int)(wid / ((int64_t)wx * ny));
+  const uint32_t tail = (xw == wx - 1 && (nx & 31)) ? ((1u << (nx & 31)) - 1u) : 0xffffffffu;  // bits inside the row
+  if (fill != nullptr) {
+    out[wid] = *fill ? tail : 0u;
+    return;
+  }
+  const uint32_t c = in[wid];
+  uint32_t r = c | (c << 1) | (c >> 1);
+  if (xw > 0) r |= in[wid - 1] >> 31;
+  if (xw + 1 < wx) r |= in[wid + 1] << 31;
+  if (y > 0) r |= in[wid - wx];
+  if (y + 1 < ny) r |= in[wid + wx];
+  const int64_t sz = (int64_t)wx * ny;
+  if (z > 0) r |= in[wid - sz];
+  if (z + 1 < nz) r |= in[wid + sz];
+  out[wid] = r & tail;
 }
 
 static constexpr int kCompThreads = 256;
-static constexpr int kCompItems = 8;
-static constexpr int kCompTile = kCompThreads * kCompItems;
+static constexpr int kCompItems = 8;                           // words per thread
+static constexpr int kCompTile = kCompThreads * kCompItems;    // words per tile
 
 __device__ __forceinline__ int comp_block_scan(int v, int* total_out) {
   __shared__ int warp_tot[kCompThreads / 32];
@@ -93,32 +129,41 @@ __device__ __forceinline__ int comp_block_scan(int v, int* total_out) {
   return woff + inc - v;
 }
 
-// flag = dilated & !mask.  pass 0: per-tile counts; pass 1: ordered (C order) index write.
+// flag words = dilated & ~mask.  pass 0: flag words + per-tile counts; pass 1: ordered (C order) index write.
 template <int PASS>
 __global__ void __launch_bounds__(kCompThreads) boundary_compact_kernel(
-    const uint8_t* __restrict__ dil, const uint8_t* __restrict__ mask, int64_t n,
-    int64_t* __restrict__ tile_counts, const int64_t* __restrict__ tile_offsets,
+    const uint32_t* __restrict__ dil, const uint32_t* __restrict__ mbits, uint32_t* __restrict__ flags, int64_t nwords,
+    int nx, int wx, int64_t* __restrict__ tile_counts, const int64_t* __restrict__ tile_offsets,
     int64_t* __restrict__ indices, int64_t cap) {
   const int64_t base = (int64_t)blockIdx.x * kCompTile + (int64_t)threadIdx.x * kCompItems;
-  int flags = 0, c = 0;
+  uint32_t f[kCompItems];
+  int c = 0;
 #pragma unroll
   for (int j = 0; j < kCompItems; ++j) {
     const int64_t i = base + j;
-    if (i < n && dil[i] != 0 && mask[i] == 0) {
-      flags |= 1 << j;
-      ++c;
-    }
+    f[j] = 0u;
+    if (i < nwords) f[j] = PASS == 0 ? (dil[i] & ~mbits[i]) : flags[i];
+    c += __popc(f[j]);
   }
   int tot;
   const int ex = comp_block_scan(c, &tot);
   if (PASS == 0) {
+#pragma unroll
+    for (int j = 0; j < kCompItems; ++j)
+      if (base + j < nwords) flags[base + j] = f[j];
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
   } else {
     int64_t o = tile_offsets[blockIdx.x] + ex;
 #pragma unroll
     for (int j = 0; j < kCompItems; ++j) {
-      if (flags & (1 << j)) {
-        if (o < cap) indices[o] = base + j;
+      uint32_t w = f[j];
+      if (w == 0u) continue;
+      const int64_t i = base + j;
+      const int64_t vox0 = (i / wx) * nx + (int64_t)(i % wx) * 32;  // linear index of the word's first voxel
+      while (w != 0u) {
+        const int b = __ffs((int)w) - 1;
+        w &= w - 1u;
+        if (o < cap) indices[o] = vox0 + b;
         ++o;
       }
     }
@@ -604,40 +649,92 @@ extern "C" int ptv_mask_gather(const uint8_t* d_mask_raw, int rnx, int rny, int 
   return PTV_OK;
 }
 
+// Workspace layout (bytes): [mask bits | dilation ping | dilation pong / flag words | tile counts, offsets, total |
+// any-fluid flag]; every word array holds wx * ny * nz uint32, wx = ceil(nx / 32).
+static int64_t boundary_words(int nx, int ny, int nz) { return (int64_t)((nx + 31) / 32) * ny * nz; }
+static int64_t boundary_tiles(int nx, int ny, int nz) { return (boundary_words(nx, ny, nz) + kCompTile - 1) / kCompTile; }
+
+extern "C" int64_t ptv_boundary_workspace_bytes(int nx, int ny, int nz) {
+  if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+  const int64_t nw = boundary_words(nx, ny, nz), nt = boundary_tiles(nx, ny, nz);
+  return 3 * ((nw * 4 + 255) & ~(int64_t)255) + (2 * nt + 2) * 8 + 256;
+}
+
+// phase 0: pack, dilate, flag, count -> *h_count (synchronises); phase 1: write the ordered indices from the
+// flag words phase 0 left in the workspace (nothing is recomputed).
+extern "C" int ptv_boundary_voxels_ws(const uint8_t* d_mask, int nx, int ny, int nz, int thickness, void* d_work,
+                                      int phase, int64_t* d_indices, int64_t cap, int64_t* h_count, void* stream_) {
+  if (!d_mask || !d_work || !h_count) { set_error("ptv_boundary_voxels_ws: NULL argument"); return PTV_ERR_INVALID; }
+  if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_boundary_voxels_ws: bad shape"); return PTV_ERR_INVALID; }
+  if (phase != 0 && phase != 1) { set_error("ptv_boundary_voxels_ws: phase must be 0 or 1"); return PTV_ERR_INVALID; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int wx = (nx + 31) / 32;
+  const int64_t nrows = (int64_t)ny * nz, nw = boundary_words(nx, ny, nz), nt = boundary_tiles(nx, ny, nz);
+  const int64_t stride = (nw * 4 + 255) & ~(int64_t)255;
+  char* wbase = reinterpret_cast<char*>(d_work);
+  uint32_t* mbits = reinterpret_cast<uint32_t*>(wbase);
+  uint32_t* ping = reinterpret_cast<uint32_t*>(wbase + stride);
+  uint32_t* pong = reinterpret_cast<uint32_t*>(wbase + 2 * stride);
+  int64_t* counts = reinterpret_cast<int64_t*>(wbase + 3 * stride);
+  int64_t* offsets = counts + nt;  // nt offsets + the total
+  int* any_fluid = reinterpret_cast<int*>(offsets + nt + 1);
+  const unsigned gw = (unsigned)((nw + 255) / 256);
+  if (phase == 0) {
+    PTV_CUDA(cudaMemsetAsync(any_fluid, 0, sizeof(int), stream));
+    pack_mask_kernel<<<gw, 256, 0, stream>>>(d_mask, nx, wx, nrows, mbits, any_fluid);
+    const uint32_t* cur = mbits;
+    int launches = 3;
+    if (thickness < 1) {  // binary_dilation(iterations < 1): repeat until stable == fill the box if any fluid exists
+      dilate_bits_kernel<<<gw, 256, 0, stream>>>(cur, nx, wx, ny, nz, ping, any_fluid);
+      cur = ping;
+      ++launches;
+    }
+    for (int it = 0; it < thickness; ++it) {
+      uint32_t* dst = (it & 1) ? pong : ping;
+      dilate_bits_kernel<<<gw, 256, 0, stream>>>(cur, nx, wx, ny, nz, dst, nullptr);
+      cur = dst;
+      ++launches;
+    }
+    // the flag words go to the buffer the last dilation did not write (pong unless it holds `cur`)
+    uint32_t* flags = cur == pong ? ping : pong;
+    boundary_compact_kernel<0><<<(unsigned)nt, kCompThreads, 0, stream>>>(cur, mbits, flags, nw, nx, wx, counts, nullptr,
+                                                                        nullptr, 0);
+    scan_i64_kernel<<<1, 1024, 0, stream>>>(counts, nt, offsets, offsets + nt);
+    // remember where the flags are for phase 1: slot after the any-fluid flag
+    const int which = flags == pong ? 1 : 0;
+    PTV_CUDA(cudaMemcpyAsync(any_fluid + 1, &which, sizeof(int), cudaMemcpyHostToDevice, stream));
+    count_launches(launches);
+    PTV_CUDA(cudaGetLastError());
+    PTV_CUDA(cudaMemcpyAsync(h_count, offsets + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    PTV_CUDA(cudaStreamSynchronize(stream));
+    return PTV_OK;
+  }
+  int which = 0;
+  PTV_CUDA(cudaMemcpyAsync(&which, any_fluid + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PTV_CUDA(cudaMemcpyAsync(h_count, offsets + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  PTV_CUDA(cudaStreamSynchronize(stream));
+  if (d_indices != nullptr && cap > 0 && *h_count > 0) {
+    uint32_t* flags = which ? pong : ping;
+    boundary_compact_kernel<1><<<(unsigned)nt, kCompThreads, 0, stream>>>(nullptr, nullptr, flags, nw, nx, wx, nullptr,
+                                                                        offsets, d_indices, cap);
+    count_launches(1);
+    PTV_CUDA(cudaGetLastError());
+  }
+  return PTV_OK;
+}
+
 extern "C" int ptv_boundary_voxels(const uint8_t* d_mask, int nx, int ny, int nz, int thickness,
                                    int64_t* d_indices, int64_t cap, int64_t* h_count, void* stream_) {
   if (!d_mask || !h_count) { set_error("ptv_boundary_voxels: NULL argument"); return PTV_ERR_INVALID; }
-  if (nx <= 0 || ny <= 0 || nz <= 0 || thickness < 0) { set_error("ptv_boundary_voxels: bad shape/thickness"); return PTV_ERR_INVALID; }
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const int64_t n = (int64_t)nx * ny * nz;
-  const int64_t ntiles = (n + kCompTile - 1) / kCompTile;
-  uint8_t *a = nullptr, *b = nullptr;
-  int64_t* counts = nullptr;
-  cudaError_t e = cudaMalloc(&a, (size_t)n);
-  if (e == cudaSuccess) e = cudaMalloc(&b, (size_t)n);
-  if (e == cudaSuccess) e = cudaMalloc(&counts, (size_t)(2 * ntiles + 1) * sizeof(int64_t));
-  int rc = PTV_OK;
-  if (e != cudaSuccess) rc = cuda_fail(e, "ptv_boundary_voxels alloc", __FILE__, __LINE__);
-  if (rc == PTV_OK) {
-    const uint8_t* cur = d_mask;
-    uint8_t* bufs[2] = {a, b};
-    for (int it = 0; it < thickness; ++it) {
-      uint8_t* dst = bufs[it & 1];
-      dilate6_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cur, nx, ny, nz, dst);
-      cur = dst;
-    }
-    count_launches(thickness + 2 + ((d_indices != nullptr && cap > 0) ? 1 : 0));
-    int64_t* offsets = counts + ntiles;
-    boundary_compact_kernel<0><<<(unsigned)ntiles, kCompThreads, 0, stream>>>(cur, d_mask, n, counts, nullptr, nullptr, 0);
-    scan_i64_kernel<<<1, 1024, 0, stream>>>(counts, ntiles, offsets, offsets + ntiles);
-    if (d_indices != nullptr && cap > 0)
-      boundary_compact_kernel<1><<<(unsigned)ntiles, kCompThreads, 0, stream>>>(cur, d_mask, n, nullptr, offsets, d_indices, cap);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_count, offsets + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) rc = cuda_fail(e, "ptv_boundary_voxels", __FILE__, __LINE__);
-  }
-  cudaFree(a); cudaFree(b); cudaFree(counts);
+  if (nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_boundary_voxels: bad shape"); return PTV_ERR_INVALID; }
+  void* work = nullptr;
+  cudaError_t e = cudaMalloc(&work, (size_t)ptv_boundary_workspace_bytes(nx, ny, nz));
+  if (e != cudaSuccess) return cuda_fail(e, "ptv_boundary_voxels alloc", __FILE__, __LINE__);
+  int rc = ptv_boundary_voxels_ws(d_mask, nx, ny, nz, thickness, work, 0, nullptr, 0, h_count, stream_);
+  if (rc == PTV_OK && d_indices != nullptr && cap > 0)
+    rc = ptv_boundary_voxels_ws(d_mask, nx, ny, nz, thickness, work, 1, d_indices, cap, h_count, stream_);
+  if (rc == PTV_OK) cudaStreamSynchronize((cudaStream_t)stream_);
+  cudaFree(work);
   return rc;
 }
 

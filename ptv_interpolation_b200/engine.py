@@ -311,13 +311,18 @@ class PTVEngine:
             mask = mask.view(torch.uint8)
         mask = mask.contiguous()
         cnt = C.c_int64()
+        nbytes = int(self.lib.ptv_boundary_workspace_bytes(nx, ny, nz))
+        if getattr(self, "_bnd_work", None) is None or self._bnd_work.numel() < nbytes:
+            self._bnd_work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)  # kept for the next call
+        work = self._bnd_work
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.ptv_boundary_voxels(_ptr(mask), nx, ny, nz, int(thickness), None, 0,
-                                                     C.byref(cnt), self._stream()))
+            # phase 0: bit-pack, dilate, flag, count; phase 1: ordered index write from the flags left in `work`
+            _cabi.check(self.lib.ptv_boundary_voxels_ws(_ptr(mask), nx, ny, nz, int(thickness), _ptr(work), 0, None, 0,
+                                                        C.byref(cnt), self._stream()))
             idx = torch.empty((cnt.value,), dtype=torch.int64, device=self.device)
             if cnt.value:
-                _cabi.check(self.lib.ptv_boundary_voxels(_ptr(mask), nx, ny, nz, int(thickness), _ptr(idx),
-                                                         cnt.value, C.byref(cnt), self._stream()))
+                _cabi.check(self.lib.ptv_boundary_voxels_ws(_ptr(mask), nx, ny, nz, int(thickness), _ptr(work), 1,
+                                                            _ptr(idx), cnt.value, C.byref(cnt), self._stream()))
         return idx
 
     def apply_mask(self, uvw, mask):

@@ -258,12 +258,24 @@ def sample_mask_on_grid(mask_raw, grid_tuple, bounds_raw, device=None):
     mask_raw = np.asarray(mask_raw)
     nz, ny, nx = mask_raw.shape
     (xmin, xmax), (ymin, ymax), (zmin, zmax) = bounds_raw
-    x, y, z = _grid_axes(grid_tuple)
+    axes = _grid_axes(grid_tuple)
     z_coords = np.linspace(zmin, zmax - 1, nz) if nz > 1 else np.array([zmin])
     y_coords = np.linspace(ymin, ymax - 1, ny) if ny > 1 else np.array([ymin])
     x_coords = np.linspace(xmin, xmax - 1, nx) if nx > 1 else np.array([xmin])
     eng = default_engine(device)
     dev = eng.device
+    if axes is None:
+        # not a rectilinear meshgrid: the reference samples whatever (X, Y, Z) holds point by point
+        # (interpolator.py:233-236) -- nearest index per point and axis, then one device gather
+        X, Y, Z = (np.asarray(a, dtype=np.float64) for a in grid_tuple)
+        idx = [torch.from_numpy(_nearest_axis_index(c, q.ravel()).astype(np.int64)).to(dev)
+               for c, q in ((x_coords, X), (y_coords, Y), (z_coords, Z))]
+        raw = (mask_raw.astype(float) > 0.5) if mask_raw.dtype != np.bool_ else mask_raw
+        raw_t = torch.from_numpy(np.ascontiguousarray(raw)).to(dev)
+        inside = (idx[0] >= 0) & (idx[1] >= 0) & (idx[2] >= 0)
+        got = raw_t[idx[2].clamp_min(0), idx[1].clamp_min(0), idx[0].clamp_min(0)] & inside
+        return got.reshape(X.shape).cpu().numpy().astype(bool)
+    x, y, z = axes
     ix = torch.from_numpy(_nearest_axis_index(x_coords, x)).to(dev)
     iy = torch.from_numpy(_nearest_axis_index(y_coords, y)).to(dev)
     iz = torch.from_numpy(_nearest_axis_index(z_coords, z)).to(dev)

@@ -558,6 +558,37 @@ def test_c4_headline_config_sampled_voxels_vs_oracle():
     assert torch.equal(part, out[:, z0:z1])
 
 
+@pytest.mark.parametrize("shape", [(9, 11, 70), (5, 8, 64), (7, 3, 31), (40, 33, 129)])
+@pytest.mark.parametrize("thickness", [0, 1, 2, 5])
+def test_boundary_particles_bitpacked_vs_oracle(shape, thickness):
+    """extract_boundary_particles on the bit-packed path (rows that are not whole words, thickness 0 ==
+    binary_dilation until stable) against the oracle port's scipy.ndimage result, element by element."""
+    rng = np.random.default_rng(shape[2] + thickness)
+    mask = rng.random(shape) > 0.55
+    mask[2:4, 1:3, 5:20] = False  # a slab of solid so that thick dilations have something to grow into
+    b = ((0, shape[2]), (0, shape[1]), (0, shape[0]))
+    for step in (1, 3):
+        got = gi.extract_boundary_particles(mask, b, sampling_step=step, thickness=thickness)
+        ref = rp.extract_boundary_particles(mask, b, sampling_step=step, thickness=thickness)
+        for g_, r_ in zip(got, ref):
+            assert np.array_equal(np.asarray(g_), np.asarray(r_))
+    empty = gi.extract_boundary_particles(np.zeros(shape, dtype=bool), b, thickness=thickness)
+    assert all(len(a) == 0 for a in empty)
+
+
+def test_sample_mask_on_arbitrary_points_vs_oracle():
+    """A grid_tuple that is not a rectilinear meshgrid (the reference accepts any X, Y, Z, interpolator.py:233-236)."""
+    rng = np.random.default_rng(5)
+    raw = rng.random((12, 10, 14)) > 0.5
+    b = ((2.0, 16.0), (0.0, 10.0), (-3.0, 9.0))
+    X = rng.uniform(0, 18, size=(4, 5, 6))
+    Y = rng.uniform(-2, 12, size=(4, 5, 6))
+    Z = rng.uniform(-5, 11, size=(4, 5, 6))
+    got = gi.sample_mask_on_grid(raw, (X, Y, Z), b)
+    ref = rp.sample_mask_on_grid(raw, (X, Y, Z), b)
+    assert got.dtype == np.bool_ and np.array_equal(got, ref)
+
+
 def test_slab_hash_matches_full_hash_and_detects_short_halos():
     """a rank that bins only its slab's particles plus a halo gets the same neighbours as with
     the whole cloud, and a halo that is too short is detected (the caller then redoes the frame)."""
