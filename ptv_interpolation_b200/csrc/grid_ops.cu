@@ -10,40 +10,58 @@ namespace ptv {
 
 // ------------------------------------------------------------------ mask gather (a2)
 // out[z,y,x] = raw[iz[z], iy[y], ix[x]] != 0, 0 where any index is -1 (out of bounds ->
-// fill_value 0, interpolator.py:230-231).  One thread = 4 consecutive x.
+// fill_value 0, interpolator.py:230-231).  A warp owns 512 consecutive x of one output row: lane l handles
+// x = 128 j + 4 l .. + 3 for j = 0..3, so every warp-wide byte gather and every 4-byte store touches one
+// 128-byte line, and a thread has sixteen independent gathers in flight (the kernel is bound by the latency
+// of its dependent loads, index -> byte, not by bytes).
+static constexpr int kMgPer = 16;
+
 __global__ void __launch_bounds__(256) mask_gather_kernel(const uint8_t* __restrict__ raw, int rnx, int rny,
                                                            const int32_t* __restrict__ mx,
                                                            const int32_t* __restrict__ my,
                                                            const int32_t* __restrict__ mz, int nx, int ny,
                                                            int nz, uint8_t* __restrict__ out) {
-  const int gx = (nx + 3) >> 2;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)gx * ny * nz;
-  if (gid >= total) return;
-  const int xg = (int)(gid % gx);
-  const int64_t row = gid / gx;
+  const int lane = threadIdx.x & 31;
+  const int gx = (nx + 32 * kMgPer - 1) / (32 * kMgPer);  // 512-wide chunks per row
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (int64_t)gx * ny * nz) return;
+  const int xc = (int)(wid % gx);
+  const int64_t row = wid / gx;
   const int y = (int)(row % ny), z = (int)(row / ny);
-  const int sz = mz[z], sy = my[y];
-  const bool rowok = sz >= 0 && sy >= 0;
-  const uint8_t* src = raw + ((int64_t)(rowok ? sz : 0) * rny + (rowok ? sy : 0)) * rnx;
-  uint8_t v[4];
+  const int xw = xc * 32 * kMgPer;
+  const bool vec = (nx & 3) == 0 && (reinterpret_cast<uintptr_t>(mx) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+  int sx[kMgPer];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int x = xg * 4 + j;
-    uint8_t r = 0;
-    if (x < nx && rowok) {
-      const int sx = mx[x];
-      if (sx >= 0) r = src[sx] != 0 ? 1 : 0;
-    }
-    v[j] = r;
-  }
-  uint8_t* dst = out + row * nx + (int64_t)xg * 4;
-  if ((nx & 3) == 0 && ((uintptr_t)out & 3) == 0) {
-    *reinterpret_cast<uchar4*>(dst) = make_uchar4(v[0], v[1], v[2], v[3]);
-  } else {
+    const int x = xw + 128 * j + 4 * lane;
+    if (vec && x + 4 <= nx) {
+      const int4 t4 = __ldg(reinterpret_cast<const int4*>(mx + x));
+      sx[4 * j] = t4.x; sx[4 * j + 1] = t4.y; sx[4 * j + 2] = t4.z; sx[4 * j + 3] = t4.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (xg * 4 + j < nx) dst[j] = v[j];
+      for (int b = 0; b < 4; ++b) sx[4 * j + b] = x + b < nx ? __ldg(mx + x + b) : -1;
+    }
+  }
+  const int sz = __ldg(mz + z), sy = __ldg(my + y);
+  const bool rowok = sz >= 0 && sy >= 0;
+  const uint8_t* src = raw + ((int64_t)(rowok ? sz : 0) * rny + (rowok ? sy : 0)) * rnx;
+  uint8_t v[kMgPer];
+#pragma unroll
+  for (int i = 0; i < kMgPer; ++i) v[i] = (rowok && sx[i] >= 0) ? __ldg(src + sx[i]) : (uint8_t)0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = xw + 128 * j + 4 * lane;
+    uint32_t w = 0u;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) w |= (v[4 * j + b] != 0 ? 1u : 0u) << (8 * b);
+    uint8_t* dst = out + row * nx + x;
+    if (vec && x + 4 <= nx) {
+      *reinterpret_cast<uint32_t*>(dst) = w;
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (x + b < nx) dst[b] = (uint8_t)(w >> (8 * b));
+    }
   }
 }
 
@@ -641,7 +659,7 @@ extern "C" int ptv_mask_gather(const uint8_t* d_mask_raw, int rnx, int rny, int 
                                void* stream) {
   if (!d_mask_raw || !d_ix || !d_iy || !d_iz || !d_out) { set_error("ptv_mask_gather: NULL argument"); return PTV_ERR_INVALID; }
   if (rnx <= 0 || rny <= 0 || rnz <= 0 || nx <= 0 || ny <= 0 || nz <= 0) { set_error("ptv_mask_gather: empty array"); return PTV_ERR_INVALID; }
-  const int64_t total = (int64_t)((nx + 3) / 4) * ny * nz;
+  const int64_t total = (int64_t)((nx + 32 * kMgPer - 1) / (32 * kMgPer)) * ny * nz * 32;  // one warp per 512 x
   mask_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       d_mask_raw, rnx, rny, d_ix, d_iy, d_iz, nx, ny, nz, d_out);
   count_launches(1);

@@ -293,8 +293,15 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
   init_point_params(p, h, queries);
   p.method = method; p.k = k; p.power = idw_power; p.smoothing = rbf_smoothing;
   p.rbf_kernel = rbf_kern; p.rbf_npoly = rbf_npoly;
-  // u, v, w are always written by the kernel: give it scratch when only the lists are wanted
-  void* scratch = nullptr;
+  // u, v, w are always written by the kernel: give it scratch when only the lists are wanted (freed on
+  // every return path, after the stream has drained)
+  struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~Scratch() { if (p) { cudaStreamSynchronize(s); cudaFree(p); } }
+  } guard;
+  guard.s = stream;
+  void*& scratch = guard.p;
   if (!want_uvw) {
     PTV_CUDA(cudaMalloc(&scratch, (size_t)queries->n * 8 * 3));
     d_u = scratch; d_v = (char*)scratch + (size_t)queries->n * 8; d_w = (char*)scratch + (size_t)queries->n * 16;
@@ -302,12 +309,10 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
   p.u = d_u; p.v = d_v; p.w = d_w;
   p.knn_idx = d_knn_idx; p.knn_dist = d_knn_dist;
   if (method == PTV_METHOD_LINEAR) {
-    const int rcl = run_linear(const_cast<ptv_hash*>(h), p, out_dtype == PTV_F32, stream);
-    if (scratch) { cudaStreamSynchronize(stream); cudaFree(scratch); }
-    return rcl;
+    return run_linear(const_cast<ptv_hash*>(h), p, out_dtype == PTV_F32, stream);
   }
   const int T = pick_heap_tile(k, method);
-  if (T == 0) { cudaFree(scratch); set_error("ptv_knn_points: k too large for shared memory (max ~580)"); return PTV_ERR_INVALID; }
+  if (T == 0) { set_error("ptv_knn_points: k too large for shared memory (max ~580)"); return PTV_ERR_INVALID; }
   if (method == PTV_METHOD_RBF) PTV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), stream));
   const_cast<ptv_hash*>(h)->last_used_stream = false;
   int rc = launch_knn_heap(p, T, out_dtype == PTV_F32, stream);
@@ -317,7 +322,6 @@ extern "C" int ptv_knn_points(const ptv_hash* h, const ptv_hash* queries, int me
     if (e != cudaSuccess) rc = cuda_fail(e, "ptv_knn_points", __FILE__, __LINE__);
     else if (*h->err_host != 0) { set_error("Singular matrix."); rc = PTV_ERR_SINGULAR; }
   }
-  if (scratch) { cudaStreamSynchronize(stream); cudaFree(scratch); }
   return rc;
 }
 
