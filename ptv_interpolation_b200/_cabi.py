@@ -117,7 +117,8 @@ def load():
     # stale library with an older ABI is never loaded silently
     from . import build as _build
     _build.build()
-    lib = C.CDLL(LIB_PATH)
+    # PTV_LIB_PATH: load another build of the same ABI instead (A/B timing of kernel variants)
+    lib = C.CDLL(os.environ.get("PTV_LIB_PATH") or LIB_PATH)
     _declare(lib)
     _lib = lib
     return lib

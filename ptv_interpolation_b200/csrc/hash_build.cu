@@ -1,7 +1,8 @@
 // Uniform-grid spatial hash of the particle cloud (replaces the cKDTree build at
 // interpolator.py:90,132).  One-pass radix (counting) sort on the cell id:
-//   bbox reduce -> cell id + histogram -> exclusive prefix scan -> scatter -> per-cell
-//   canonical order (by original index) + 32-byte record fill.
+//   bbox reduce (one launch, last block folds) -> cell id + histogram + slot-in-cell + original-order values
+//   -> exclusive prefix scan -> scatter (no atomics: start + slot) -> per-cell canonical order (by original
+//   index) -> 32-byte record fill.  Seven launches.
 // All kernels are HBM/L2-bound streaming passes over the particle arrays; algorithmic traffic
 // is ~112 B/particle.
 #include <math.h>
@@ -24,7 +25,9 @@ static constexpr int kScanTile = kScanThreads * kScanItems;
 // partial layout per block: minx,miny,minz,maxx,maxy,maxz,bad
 __global__ void __launch_bounds__(kBboxThreads) bbox_partial_kernel(const double* __restrict__ pts,
                                                                      int64_t n,
-                                                                     double* __restrict__ partial) {
+                                                                     double* __restrict__ partial,
+                                                                     unsigned* __restrict__ done_count,
+                                                                     double* __restrict__ out) {
   double mn[3] = {INFINITY, INFINITY, INFINITY};
   double mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   double bad = 0.0;
@@ -64,18 +67,23 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_partial_kernel(const double
       acc = (q < 3) ? fmin(acc, sh[q][w2]) : fmax(acc, sh[q][w2]);
     partial[blockIdx.x * 7 + q] = acc;
   }
-}
-
-__global__ void bbox_final_kernel(const double* __restrict__ partial, int nblocks,
-                                  double* __restrict__ out) {
-  const int q = threadIdx.x;
-  if (q >= 7) return;
-  double acc = partial[q];
-  for (int b = 1; b < nblocks; ++b) {
-    double v = partial[b * 7 + q];
-    acc = (q < 3) ? fmin(acc, v) : fmax(acc, v);
+  // the last block to arrive folds the per-block partials (no second launch)
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(done_count, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last && threadIdx.x < 7) {
+    const int q = threadIdx.x;
+    const volatile double* vp = partial;
+    double acc = vp[q];
+    for (int b = 1; b < (int)gridDim.x; ++b) {
+      const double v = vp[b * 7 + q];
+      acc = (q < 3) ? fmin(acc, v) : fmax(acc, v);
+    }
+    out[q] = acc;
+    if (q == 0) *done_count = 0u;  // ready for the next build
   }
-  out[q] = acc;
 }
 
 // ------------------------------------------------------------------------------ binning
@@ -88,10 +96,21 @@ __global__ void __launch_bounds__(256) cell_count_kernel(const double* __restric
                                                           double ox, double oy, double oz,
                                                           double inv_cell, int cnx, int cny, int cnz,
                                                           double zlo, double zhi,
+                                                          const double* __restrict__ vals_in,
+                                                          Value4* __restrict__ vals,
                                                           int32_t* __restrict__ cid,
+                                                          int32_t* __restrict__ slot,
                                                           int32_t* __restrict__ counts) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  {  // (u, v, w, 0) in ORIGINAL order for the gathers by particle row
+    Value4 v;
+    v.u = vals_in[i * 3 + 0];
+    v.v = vals_in[i * 3 + 1];
+    v.w = vals_in[i * 3 + 2];
+    v.pad = 0.0;
+    vals[i] = v;
+  }
   const double pz = pts[i * 3 + 2];
   if (pz < zlo || pz > zhi) {  // slab hash: outside the binned z-range
     cid[i] = -1;
@@ -102,7 +121,7 @@ __global__ void __launch_bounds__(256) cell_count_kernel(const double* __restric
   const int cz = cell_coord(pz, oz, inv_cell, cnz);
   const int32_t c = (cz * cny + cy) * cnx + cx;
   cid[i] = c;
-  atomicAdd(&counts[c], 1);
+  slot[i] = atomicAdd(&counts[c], 1);  // arrival order inside the cell; made canonical after the scatter
 }
 
 // ------------------------------------------------------------------------------ scan
@@ -178,14 +197,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(int32_t* __res
 // ------------------------------------------------------------------------------ scatter
 __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict__ cid, int64_t n,
                                                        const int32_t* __restrict__ cell_start,
-                                                       int32_t* __restrict__ cell_fill,
+                                                       const int32_t* __restrict__ slot,
                                                        int32_t* __restrict__ sorted_idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int32_t c = cid[i];
   if (c < 0) return;
-  const int32_t pos = cell_start[c] + atomicAdd(&cell_fill[c], 1);
-  sorted_idx[pos] = (int32_t)i;
+  sorted_idx[cell_start[c] + slot[i]] = (int32_t)i;
 }
 
 // Canonical order inside each cell (ascending original index, == a stable sort on the cell id)
@@ -269,24 +287,12 @@ __global__ void __launch_bounds__(256) fill_records_kernel(const double* __restr
   vals_s32[p] = make_float4((float)v.u, (float)v.v, (float)v.w, 0.0f);
 }
 
-__global__ void __launch_bounds__(256) fill_values_kernel(const double* __restrict__ vals_in, int64_t n,
-                                                           Value4* __restrict__ vals) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Value4 v;
-  v.u = vals_in[i * 3 + 0];
-  v.v = vals_in[i * 3 + 1];
-  v.w = vals_in[i * 3 + 2];
-  v.pad = 0.0;
-  vals[i] = v;
-}
-
 static int ensure_capacity(ptv_hash* h, int64_t n, int64_t ncells) {
   if (n > h->cap_n) {
     const int64_t cap = n + n / 8 + 1024;
-    cudaFree(h->rec); cudaFree(h->vals); cudaFree(h->cid); cudaFree(h->sorted_idx);
+    cudaFree(h->rec); cudaFree(h->vals); cudaFree(h->cid); cudaFree(h->sorted_idx); cudaFree(h->slot);
     cudaFree(h->vals_s64); cudaFree(h->vals_s32);
-    h->rec = nullptr; h->vals = nullptr; h->cid = nullptr; h->sorted_idx = nullptr;
+    h->rec = nullptr; h->vals = nullptr; h->cid = nullptr; h->sorted_idx = nullptr; h->slot = nullptr;
     h->vals_s64 = nullptr; h->vals_s32 = nullptr;
     h->cap_n = 0;
     PTV_CUDA(cudaMalloc(&h->rec, cap * sizeof(ParticleRec)));
@@ -295,6 +301,7 @@ static int ensure_capacity(ptv_hash* h, int64_t n, int64_t ncells) {
     PTV_CUDA(cudaMalloc(&h->vals_s32, cap * sizeof(float4)));
     PTV_CUDA(cudaMalloc(&h->cid, cap * sizeof(int32_t)));
     PTV_CUDA(cudaMalloc(&h->sorted_idx, cap * sizeof(int32_t)));
+    PTV_CUDA(cudaMalloc(&h->slot, cap * sizeof(int32_t)));
     h->cap_n = cap;
   }
   if (ncells + 1 > h->cap_cells) {
@@ -361,6 +368,7 @@ extern "C" int ptv_hash_create(ptv_hash** out) {
   PTV_CUDA(cudaGetDevice(&dev));
   ptv_hash* h = new ptv_hash();
   cudaError_t e = cudaMalloc(&h->bbox_dev, (kBboxBlocks * 7 + 8) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(h->bbox_dev, 0, 8 * sizeof(double));  // [7]: the bbox kernel's arrival counter
   if (e == cudaSuccess) e = cudaMallocHost(&h->bbox_host, 8 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->err_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMallocHost(&h->err_host, sizeof(int));
@@ -375,7 +383,7 @@ extern "C" int ptv_hash_create(ptv_hash** out) {
 
 extern "C" int ptv_hash_destroy(ptv_hash* h) {
   if (!h) return PTV_OK;
-  cudaFree(h->rec); cudaFree(h->vals); cudaFree(h->cid); cudaFree(h->sorted_idx);
+  cudaFree(h->rec); cudaFree(h->vals); cudaFree(h->cid); cudaFree(h->sorted_idx); cudaFree(h->slot);
   cudaFree(h->vals_s64); cudaFree(h->vals_s32);
   cudaFree(h->cell_start); cudaFree(h->cell_fill); cudaFree(h->scan_tmp);
   cudaFree(h->bbox_dev);
@@ -442,9 +450,9 @@ static int build_impl(ptv_hash* h, const double* d_points, const double* d_value
 
   // 1. bounding box (and finiteness) of the cloud
   double* partial = h->bbox_dev + 8;
-  bbox_partial_kernel<<<kBboxBlocks, kBboxThreads, 0, stream>>>(d_points, n, partial);
-  bbox_final_kernel<<<1, 32, 0, stream>>>(partial, kBboxBlocks, h->bbox_dev);
-  count_launches(2);
+  bbox_partial_kernel<<<kBboxBlocks, kBboxThreads, 0, stream>>>(d_points, n, partial,
+                                                                reinterpret_cast<unsigned*>(h->bbox_dev + 7), h->bbox_dev);
+  count_launches(1);
   PTV_CUDA(cudaGetLastError());
   PTV_CUDA(cudaMemcpyAsync(h->bbox_host, h->bbox_dev, 7 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   PTV_CUDA(cudaStreamSynchronize(stream));
@@ -483,10 +491,11 @@ static int build_impl(ptv_hash* h, const double* d_points, const double* d_value
 
   // 2. cell ids + histogram
   PTV_CUDA(cudaMemsetAsync(h->cell_start, 0, (ncells + 1) * sizeof(int32_t), stream));
-  PTV_CUDA(cudaMemsetAsync(h->cell_fill, 0, (ncells + 1) * sizeof(int32_t), stream));
+  PTV_CUDA(cudaMemsetAsync(h->cell_fill + ncells, 0, sizeof(int32_t), stream));  // max_count slot
   const int nb_p = (int)((n + 255) / 256);
   cell_count_kernel<<<nb_p, 256, 0, stream>>>(d_points, n, h->origin[0], h->origin[1], h->origin[2],
-                                              1.0 / cell, dims[0], dims[1], dims[2], zlo, zhi, h->cid, h->cell_start);
+                                              1.0 / cell, dims[0], dims[1], dims[2], zlo, zhi, d_values, h->vals, h->cid,
+                                              h->slot, h->cell_start);
   // 3. exclusive scan over ncells+1 entries (last entry becomes n)
   const int64_t nscan = ncells + 1;
   const int nb_s = (int)((nscan + kScanTile - 1) / kScanTile);
@@ -494,14 +503,13 @@ static int build_impl(ptv_hash* h, const double* d_points, const double* d_value
   scan_blocksums_kernel<<<1, kScanThreads, 0, stream>>>(h->scan_tmp, nb_s);
   scan_apply_kernel<<<nb_s, kScanThreads, 0, stream>>>(h->cell_start, nscan, h->scan_tmp);
   // 4. scatter, canonical order, records, values
-  scatter_kernel<<<nb_p, 256, 0, stream>>>(h->cid, n, h->cell_start, h->cell_fill, h->sorted_idx);
+  scatter_kernel<<<nb_p, 256, 0, stream>>>(h->cid, n, h->cell_start, h->slot, h->sorted_idx);
   int32_t* max_count = h->cell_fill + ncells;  // zeroed above
   cell_canonical_kernel<<<(int)((ncells + 255) / 256), 256, 0, stream>>>(h->cell_start, ncells,
                                                                         h->sorted_idx, max_count);
   fill_records_kernel<<<nb_p, 256, 0, stream>>>(d_points, d_values, h->sorted_idx, n, h->cell_start + ncells, h->rec,
                                                 h->vals_s64, h->vals_s32);
-  fill_values_kernel<<<nb_p, 256, 0, stream>>>(d_values, n, h->vals);
-  count_launches(8);
+  count_launches(7);
   PTV_CUDA(cudaGetLastError());
   h->max_cell_count = -1;  // fetched lazily by ptv_hash_info
   h->built = true;

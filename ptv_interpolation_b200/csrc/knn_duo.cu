@@ -53,6 +53,7 @@ struct __align__(16) WarpScan {  // iterator over the cell list around the warp'
 };
 static constexpr size_t kColBytes = (size_t)kDNB * 32 * 2 * sizeof(uint16_t);  // 8 KB: [bin][lane][voxel]
 static_assert(kColBytes >= (size_t)2 * kDList * 32 * 8, "lists must fit under the histograms");
+static_assert(kDList <= 16, "duo_select packs the list slot into four bits");
 static constexpr size_t kOffS32 = kColBytes;
 static constexpr size_t kOffS64 = kOffS32 + 2 * kDCH * sizeof(float4);
 static constexpr size_t kOffVal = kOffS64 + 2 * kDCH * sizeof(ParticleRec);
@@ -414,19 +415,21 @@ __device__ __forceinline__ Value4 sorted_value(const HashGrid& g, int spos, int 
 }
 
 // The `nd` smallest (d2, row) entries of one voxel's crossing-bin list, moved to the front of the list.
-// Keys are float32 offsets from E_lo (monotone in the exact key); entries whose offsets are equal across
-// the cut (exact ties, or keys closer than float32 resolves) are ordered by the exact key computed from
-// the caller's particle rows.
+// Keys are float32 offsets from E_lo (monotone in the exact key); entries whose offsets coincide across the
+// cut (exact ties, or keys closer than the packed float32 resolves) are ordered by the exact key computed
+// from the cell-sorted records.
 __device__ __noinline__ void duo_select(const HashGrid* gs, float* lk, int* li, int nl, int nd, double qx, double qy,
                                         double qz) {
+  // selection on packed integers: the offsets are non-negative floats, so their bit patterns order like the
+  // values; the four lowest mantissa bits give way to the list slot, which makes every round one
+  // load + integer-min per entry (keys that differ only in those bits count as tied, see below)
+  auto packed = [&](int j) { return (int)((__float_as_uint(lk[j * 32]) & ~15u) | (unsigned)j); };
   for (int i = 0; i < nd; ++i) {
-    int best = i;
-    float bk = lk[i * 32];
-    for (int j = i + 1; j < nl; ++j) {
-      const float kj = lk[j * 32];
-      if (kj < bk) { best = j; bk = kj; }
-    }
+    int m = packed(i);
+    for (int j = i + 1; j < nl; ++j) m = min(m, packed(j));
+    const int best = m & 15;
     if (best != i) {
+      const float bk = lk[best * 32];
       const int bi = li[best * 32];
       lk[best * 32] = lk[i * 32];
       li[best * 32] = li[i * 32];
@@ -435,18 +438,19 @@ __device__ __noinline__ void duo_select(const HashGrid* gs, float* lk, int* li, 
     }
   }
   if (nd <= 0 || nd >= nl) return;
-  const float cut = lk[(nd - 1) * 32];
-  float rest = INFINITY;
-  for (int j = nd; j < nl; ++j) rest = fminf(rest, lk[j * 32]);
+  const unsigned cut = __float_as_uint(lk[(nd - 1) * 32]) & ~15u;
+  unsigned rest = 0xffffffffu;
+  for (int j = nd; j < nl; ++j) rest = min(rest, __float_as_uint(lk[j * 32]) & ~15u);
   if (rest != cut) return;
+  auto tied = [&](int j) { return (__float_as_uint(lk[j * 32]) & ~15u) == cut; };
   int first = nd - 1;
-  while (first > 0 && lk[(first - 1) * 32] == cut) --first;
-  // entries [first, nl) with offset == cut compete for the slots [first, nd)
+  while (first > 0 && tied(first - 1)) --first;
+  // entries [first, nl) tied with the cut compete for the slots [first, nd): exact (d2, row) order
   for (int i = first; i < nd; ++i) {
     int best = -1, bi = 0;
     double bk = 0.0;
     for (int j = i; j < nl; ++j) {
-      if (lk[j * 32] != cut) continue;
+      if (!tied(j)) continue;
       int ij;
       const double kj = exact_from_rec(*gs, qx, qy, qz, li[j * 32], ij);
       if (best < 0 || key_greater(bk, bi, kj, ij)) { best = j; bk = kj; bi = ij; }
@@ -764,7 +768,8 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
 #pragma unroll 8
       for (int b = 0; b < kDNB; ++b) hw[b * 32] = 0u;
     }
-    bool finished = false, whole = false;
+    bool finished = false;
+    DuoThr th[2];  // thresholds of the last stage scanned
     {
       float qa[2][3], qb[2];  // -2 q / binw and |q|^2 / binw: bin index = qa.c + |c|^2 / binw + qb
 #pragma unroll
@@ -807,42 +812,41 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
           }
         }
         if (kStats && lane == 0) duo_count(&wcnt[0], (unsigned long long)staged * ccnt);
-        // stop test: >= k particles in bins that lie entirely inside the scanned radius
+        // stop test: >= k particles in bins that lie entirely inside the scanned radius -- the same scan that
+        // finds the crossing bin (its upper edge inside the scanned radius <=> that many bins are complete)
         bool done = true;
-        if (!last) {
-          const int nfull = min(kEdges[stage], kDNB - 1);
-          done = (!ok[0] || duo_hist_cum(hist, nfull) >= k) && (!ok[1] || duo_hist_cum(hist + 1, nfull) >= k);
+        {
+          const double rin = sc->R - 1e-6 * g.cell;
+          const double rin2 = last ? -1.0 : rin * rin;
+#pragma unroll
+          for (int v = 0; v < 2; ++v)
+            if (ok[v]) {
+              th[v] = duo_thresholds(hist + v, k, binw, rin2);
+              done = done && !(th[v].flags & 2);
+            }
         }
         if (__all_sync(kFull, done) || last) {
           finished = true;
-          whole = last;
           if (kStats && lane == 0 && stage > 0) duo_count(&p.stats[4 + stage], 1ULL);
           break;
         }
       }
     }
-    if (!finished) {  // the k-th neighbour of some voxel is beyond the histogram range: those go to the exact
-                      // kernel, the others are classified on what was scanned
-      if (ok[0] && duo_hist_cum(hist, kDNB - 1) < k) fail_voxel(0, 2);
-      if (ok[1] && duo_hist_cum(hist + 1, kDNB - 1) < k) fail_voxel(1, 2);
-      if (!__any_sync(kFull, ok[0] || ok[1])) continue;
-    }
-
-    // ---- thresholds from the crossing bin
+    // ---- thresholds from the crossing bin (found by the last stage's scan).  A voxel whose crossing bin is
+    //      not inside the scanned radius -- only possible when the three stages were not enough: the k-th
+    //      neighbour is beyond the histogram range -- goes to the exact kernel; the others are classified on
+    //      what was scanned.
     double e_lo[2] = {0.0, 0.0}, e_hi[2] = {0.0, 0.0};
     {
-      const double rin = sc->R - 1e-6 * g.cell;
-      const double rin2 = whole ? -1.0 : rin * rin;
-      DuoThr th[2];
       bool crowded[2] = {false, false};
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
         if (ok[v]) {
-          th[v] = duo_thresholds(hist + v, k, binw, rin2);
-          if (th[v].flags & 2) fail_voxel(v, 3);
+          if (th[v].flags & 2) fail_voxel(v, finished ? 3 : 2);
           crowded[v] = ok[v] && (th[v].flags & 1);
         }
       }
+      if (!__any_sync(kFull, ok[0] || ok[1])) continue;
       // ---- phase A2 (rare): a crossing bin that holds more particles than the short list is
       //      re-histogrammed with kDNB sub-bins; phase B still verifies the result exactly
       if (__any_sync(kFull, crowded[0] || crowded[1])) {

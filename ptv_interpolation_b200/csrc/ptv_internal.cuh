@@ -72,6 +72,7 @@ struct ptv_hash {
   float4* vals_s32 = nullptr;
   int32_t* cid = nullptr;
   int32_t* sorted_idx = nullptr;
+  int32_t* slot = nullptr;        // arrival order of each particle inside its cell (count pass)
   int32_t* cell_start = nullptr;  // ncells+1
   int32_t* cell_fill = nullptr;   // ncells
   int32_t* scan_tmp = nullptr;
