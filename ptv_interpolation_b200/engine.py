@@ -193,7 +193,9 @@ class PTVEngine:
         if tuple(host_out.shape) != (3, nz, ny, nx) or host_out.dtype != dev_out.dtype:
             raise ValueError("host_out must be a (3, nz, ny, nx) CPU tensor of the output dtype")
         if chunks is None:
-            chunks = max(1, min(16, nz // 16))
+            # chunks of >= 32 planes (one region layer of the streaming kernel); many small ones keep the
+            # drain of the LAST chunk -- the part that cannot overlap anything -- short
+            chunks = max(1, min(32, nz // 32))
         if not hasattr(self, "copy_stream"):
             self.copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
