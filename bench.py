@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-all-voxel", action="store_true")
+    ap.add_argument("--no-halo-overlap", action="store_true", help="one interpolation launch per slab, halos afterwards")
     ap.add_argument("--cpu-sample-voxels", type=int, default=400_000)
     ap.add_argument("--parity-voxels", type=int, default=4000)
     ap.add_argument("--c5-frames", type=int, default=64)
@@ -364,7 +365,9 @@ def run_b200(args):
     # ---- synthetic inputs, identical on every rank (same seed, same device type)
     cfg = synthetic.make_config(args.workload, device=dev)
     n, method, k = cfg["n"], cfg["method"], cfg["k"]
-    comm = SlabComm(n)
+    # slabs balanced by pore voxels per plane (solid voxels cost nothing); every rank computes the same cuts
+    plane_pore = cfg["mask"].sum(dim=(1, 2)).cpu().tolist()
+    comm = SlabComm(n, plane_weights=plane_pore)
     z0, z1 = comm.z0, comm.z1
     total_pore = int(cfg["mask"].sum())
     mask_slab = cfg["mask"][z0:z1].contiguous().view(torch.uint8)
@@ -397,7 +400,8 @@ def run_b200(args):
         if record:
             e[0].record()
         res = hot_path_step(eng, points, values, ax, ax, ax, mask_slab, comm, method=method, k=k, out=out,
-                            mark=(lambda label: e[marks[label]].record()) if record else None)
+                            mark=(lambda label: e[marks[label]].record()) if record else None,
+                            overlap_halos=not args.no_halo_overlap)
         if record:
             e[3].record()
         keep.update(div=res.div, res=res)
@@ -667,7 +671,7 @@ def run_b200(args):
                                            "every voxel (no mask)"}
 
     config = core_config(args.workload, n, npart, method, k, total_pore)
-    details = {"porosity": total_pore / n ** 3, "parallelism": f"z-slab x{world}", "slab_planes_rank0": nzl,
+    details = {"porosity": total_pore / n ** 3, "parallelism": f"z-slab x{world}, cuts balanced by pore voxels per plane", "slab_planes_rank0": nzl,
                "l2_policy": "inputs_larger_than_L2" if nzl * n * n * 13 > 126e6 else "small_workload_fits_L2",
                "mask_skip": True, "all_voxels_per_sec": n ** 3 / (ms_per_step * 1e-3),
                "all_voxel_ms": all_voxel_ms,

@@ -882,7 +882,17 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
     }
     __syncwarp();  // the histograms are dead: the columns now hold the lists
 
-    // ---- phase B: exact classification of the final region
+    // ---- phase B: exact classification.  Every key below E_hi has to be seen, nothing more: the region shrinks
+    //      to the box (+) the largest sqrt(E_hi) of the warp's voxels (never larger than what phase A scanned)
+    {
+      float rb = 0.0f;
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+        if (ok[v]) rb = fmaxf(rb, __double2float_ru(sqrt(e_hi[v])));
+      rb = __int_as_float(__reduce_max_sync(kFull, __float_as_int(rb)));  // non-negative floats order like ints
+      const double RB = fmin((double)rb * (1.0 + 1e-6) + 1e-6 * g.cell, sc->R);
+      duo_begin_scan(gs, sc, RB, 0);
+    }
     // float32 error of the expanded squared distance: coordinates are below `half` in magnitude
     const float half = (float)(sc->R + fmax(sc->hi[0] - sc->lo[0], fmax(sc->hi[1] - sc->lo[1], sc->hi[2] - sc->lo[2])) +
                                g.cell) * 1.000001f;
@@ -910,7 +920,6 @@ __global__ void __launch_bounds__(kDT, sizeof(OutT) == 4 ? 4 : 3) knn_duo_kernel
     }
     const bool p2 = p.power == 2.0;
     unsigned nexact = 0u;
-    duo_restart_scan(sc);
     int staged_b = 0;
     for (;;) {
       const int m = duo_next_chunk<OutT>(gs, wb, 1);

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["slab_range", "SlabComm"]
+__all__ = ["slab_range", "slab_range_weighted", "SlabComm"]
 
 
 def slab_range(nz: int, world: int, rank: int):
@@ -21,17 +21,47 @@ def slab_range(nz: int, world: int, rank: int):
     return z0, z0 + base + (1 if rank < rem else 0)
 
 
+def slab_range_weighted(weights, world: int, rank: int):
+    """Contiguous z-planes [z0, z1) of ``rank`` such that every rank gets about the same share of
+    ``sum(weights)`` (weights[z] = work of plane z, e.g. its pore-voxel count: solid voxels cost nothing) and
+    at least one plane.  Deterministic: every rank computes the same cuts from the same weights."""
+    w = [float(x) for x in weights]
+    nz = len(w)
+    if world > nz:
+        raise ValueError("more ranks than z-planes")
+    total = sum(w)
+    if total <= 0.0:
+        return slab_range(nz, world, rank)
+    cuts, acc, z = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        # advance while the plane's midpoint lies below the target; keep one plane for every rank on both sides
+        while z < nz - (world - r) and (z < cuts[-1] + 1 or acc + 0.5 * w[z] < target):
+            acc += w[z]
+            z += 1
+        cuts.append(z)
+    cuts.append(nz)
+    return cuts[rank], cuts[rank + 1]
+
+
 class SlabComm:
     """Halo exchange + reductions for one slab decomposition.  With world == 1 every method is a
     no-op that returns the local data."""
 
-    def __init__(self, nz: int, group=None):
+    def __init__(self, nz: int, group=None, plane_weights=None):
+        """``plane_weights`` (length nz, identical on every rank; e.g. pore voxels per z-plane) balances the
+        slabs by work instead of by plane count."""
         self.group = group
         self.on = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if self.on else 1
         self.rank = dist.get_rank(group) if self.on else 0
         self.nz = nz
-        self.z0, self.z1 = slab_range(nz, self.world, self.rank)
+        if plane_weights is not None and self.world > 1:
+            if len(plane_weights) != nz:
+                raise ValueError("plane_weights must have one entry per z-plane")
+            self.z0, self.z1 = slab_range_weighted(plane_weights, self.world, self.rank)
+        else:
+            self.z0, self.z1 = slab_range(nz, self.world, self.rank)
         # neighbours that own at least one plane
         self.lower = self.rank - 1 if self.rank > 0 else None
         self.upper = self.rank + 1 if self.rank + 1 < self.world else None

@@ -24,7 +24,7 @@ class StepResult:
 
 def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, comm: SlabComm, method="idw",
                   k=50, idw_power=2.0, spacing=(1.0, 1.0, 1.0), out=None, out_dtype=torch.float32,
-                  rebuild=True, mark=None) -> StepResult:
+                  rebuild=True, mark=None, overlap_halos=True) -> StepResult:
     """One pass over one PTV frame for this rank's z-slab.  ``ax_z`` is the FULL z axis; the slab is
     comm.z0:comm.z1.  ``mask_slab`` is the (nz_local, ny, nx) uint8 pore mask of the slab.  ``mark(label)``
     is called after the hash build ("built") and after the last interpolation launch ("interpolated")."""
@@ -33,7 +33,11 @@ def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, c
     if slab_hash:
         # north_star: "each GPU holds its slab's particles plus a halo" -- bin only z within the slab +- a halo
         # of expected k-neighbour radii; a search that leaves the range is detected below
-        eng.build_slab(points, values, float(ax_z[comm.z0]), float(ax_z[comm.z1 - 1]), k)
+        key = (ax_z.data_ptr(), comm.z0, comm.z1)
+        if getattr(comm, "_zrange_key", None) != key:  # two host reads, once per grid (not per frame)
+            comm._zrange = (float(ax_z[comm.z0]), float(ax_z[comm.z1 - 1]))
+            comm._zrange_key = key
+        eng.build_slab(points, values, min(comm._zrange), max(comm._zrange), k)
     elif rebuild:
         eng.build(points, values)
     mark("built")
@@ -42,7 +46,7 @@ def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, c
     nx, ny = ax_x.numel(), ax_y.numel()
     kw = dict(method=method, k=k, idw_power=idw_power)
     edge = 32  # z-extent of one CTA region of the streaming kernel
-    if comm.world > 1 and nzl >= 3 * edge:
+    if overlap_halos and comm.world > 1 and nzl >= 3 * edge:
         # the slab's first and last planes feed the neighbours' divergence stencils: interpolate the two
         # boundary chunks first, start the halo exchange, and let it travel while the interior is searched
         if out is None:
@@ -72,5 +76,6 @@ def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, c
         if float(acc[-1].item()) > 0.0:
             eng.build(points, values)
             return hot_path_step(eng, points, values, ax_x, ax_y, ax_z, mask_slab, comm, method=method, k=k,
-                                 idw_power=idw_power, spacing=spacing, out=uvw, out_dtype=out_dtype, rebuild=False)
+                                 idw_power=idw_power, spacing=spacing, out=uvw, out_dtype=out_dtype, rebuild=False,
+                                 overlap_halos=overlap_halos)
     return StepResult(uvw, div, q_xy, q_xz, q_yz, stats[0] / stats[1], stats[1])

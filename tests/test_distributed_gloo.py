@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import reference_port as rp
-from ptv_interpolation_b200.distributed import SlabComm, slab_range
+from ptv_interpolation_b200.distributed import SlabComm, slab_range, slab_range_weighted
 
 
 def _free_port():
@@ -32,6 +32,22 @@ def test_slab_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
             sizes = [b - a for a, b in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_slab_range_weighted_balances_work():
+    rng = np.random.default_rng(0)
+    for nz, world in ((16, 2), (100, 8), (1024, 8), (9, 9), (40, 3)):
+        w = rng.random(nz) * (1.0 + np.sin(np.arange(nz) / 3.0) ** 2)
+        cuts = [slab_range_weighted(w, world, r) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == nz
+        assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+        assert all(b > a for a, b in cuts)
+        if nz >= 10 * world:
+            work = np.array([w[a:b].sum() for a, b in cuts])
+            assert work.max() <= w.sum() / world + w.max()  # within one plane of the ideal share
+    assert slab_range_weighted(np.zeros(12), 3, 1) == slab_range(12, 3, 1)
+    with pytest.raises(ValueError):
+        slab_range_weighted(np.ones(3), 4, 0)
 
 
 def _worker(rank, world, port, shape, tmp):
