@@ -141,7 +141,18 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
       const int r = lane + 32 * q;
       if (r < k) {
         double* row = A + r * LD;
-        for (int j = 0; j < k; ++j) {
+        int j = 0;
+        for (; j + 4 <= k; j += 4) {  // four entries per trip: the loads of all four come before the stores
+          double d2v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double dx = yx[q] - Y[(j + u) * 3 + 0], dy = yy[q] - Y[(j + u) * 3 + 1], dz = yz[q] - Y[(j + u) * 3 + 2];
+            d2v[u] = (dx * dx + dy * dy) + dz * dz;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) row[j + u] = rbf_phi_from_d2(kern, d2v[u]);
+        }
+        for (; j < k; ++j) {
           const double dx = yx[q] - Y[j * 3 + 0], dy = yy[q] - Y[j * 3 + 1], dz = yz[q] - Y[j * 3 + 2];
           row[j] = rbf_phi_from_d2(kern, (dx * dx + dy * dy) + dz * dz);
         }
@@ -198,7 +209,18 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
           double* row = A + r * LD;
           const double f = row[c] / piv;
           if (f != 0.0) {
-            for (int j = c + 1; j < n; ++j) row[j] -= f * prow[j];
+            // the lane's row is never the pivot row, but the compiler cannot know: four columns per trip with
+            // every load issued before the first store, so the shared-memory round trips overlap
+            int j = c + 1;
+            for (; j + 4 <= n; j += 4) {
+              const double p0 = prow[j], p1 = prow[j + 1], p2 = prow[j + 2], p3 = prow[j + 3];
+              const double r0 = row[j], r1 = row[j + 1], r2 = row[j + 2], r3 = row[j + 3];
+              row[j] = r0 - f * p0;
+              row[j + 1] = r1 - f * p1;
+              row[j + 2] = r2 - f * p2;
+              row[j + 3] = r3 - f * p3;
+            }
+            for (; j < n; ++j) row[j] -= f * prow[j];
             B[r * 3 + 0] -= f * B[best * 3 + 0];
             B[r * 3 + 1] -= f * B[best * 3 + 1];
             B[r * 3 + 2] -= f * B[best * 3 + 2];
