@@ -201,6 +201,12 @@ int ptv_divergence_flux(const void* d_u, const void* d_v, const void* d_w, const
                         const void* d_w_above, const uint8_t* d_mask_above, int dtype, void* d_div,
                         double* d_absdiv_sum, double* d_qxy, double* d_qxz, double* d_qyz, void* stream);
 
+/* ---- self-test of the stencil kernels' division: the kernels divide by the grid spacings through a
+ *      correctly-rounded reciprocal sequence instead of the IEEE division instruction sequence (bit-identity
+ *      with physics.py:26-53 and np.gradient depends on it).  Runs n pseudo-random numerators against
+ *      divisor h on the device and returns how many results differ from the IEEE quotient (must be 0). */
+int ptv_selftest_division(double h, int64_t n, uint64_t seed, int64_t* mismatches);
+
 /* ---- shear-rate magnitude and vorticity magnitude: replaces compute_strain_rate / compute_vorticity
  *      (velocity_analysis.py:10-63, 94-120; nine np.gradient stencils).  d_mask nullable; either output
  *      nullable. ------------------------------------------------------------------------------- */

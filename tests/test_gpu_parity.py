@@ -131,13 +131,29 @@ def test_divergence_flux_golden(golden_dir):
     assert d32.dtype == np.float32 and np.array_equal(d32, ref.astype(np.float32))
 
 
-@pytest.mark.parametrize("shape", [(11, 9, 7), (6, 10, 16), (5, 33, 1028), (3, 4, 2052)])
+def test_exact_division_by_spacing():
+    """The stencil kernels divide by the grid spacing with a reciprocal + two FMA corrections; every result must
+    be the IEEE quotient (bit-identity with physics.py:26-53 / np.gradient rests on it)."""
+    import ctypes as C
+    from ptv_interpolation_b200 import _cabi
+    lib = _cabi.load()
+    for h in (2.00625, 4.0125, 1.25, 0.75, 3.0, 0.1, 1e-3, 7.0, -2.00625, 1.9999999999999998, 1.0000000000000002,
+              1.0 / 3.0, 123456.789):
+        bad = C.c_int64(-1)
+        _cabi.check(lib.ptv_selftest_division(h, 1 << 28, 12345, C.byref(bad)))
+        assert bad.value == 0, h
+
+
+# nx % 16 == 0 -> bulk-async row pipeline (one chunk, two chunks with x halos, ragged last chunk, > 256 rows per
+# z-plane so a plane is swept by several CTAs); the other shapes take the direct-load kernels
+@pytest.mark.parametrize("shape", [(11, 9, 7), (6, 10, 16), (5, 33, 1028), (3, 4, 2052), (4, 37, 1040), (6, 5, 2080),
+                                   (7, 300, 48), (2, 3, 1024)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_fused_divergence_flux(shape, dtype):
     rng = np.random.default_rng(shape[2])
     u, v, w = (rng.normal(size=shape).astype(dtype) for _ in range(3))
     m = rng.random(shape) > 0.35
-    h = (1.25, 0.75, 2.0) if shape[0] > 5 else (1.0, 1.0, 1.0)
+    h = (1.25, 0.75, 2.00625) if shape[0] > 5 else (1.0, 1.0, 1.0)
     eng = PTVEngine()
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     div, st, qxy, qxz, qyz = eng.divergence_flux(t(u), t(v), t(w), t(m), *h)
