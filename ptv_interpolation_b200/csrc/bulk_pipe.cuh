@@ -34,9 +34,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // Needs t, h and t / h well inside the normal range (checked: by the caller for h, here for t); everything
 // else takes the IEEE division.  ptv_selftest_division compares it with __ddiv_rn on the device.
 __device__ __forceinline__ double div_by_spacing(double t, double h, double rh) {
-  if (t == 0.0) return h > 0.0 ? t : -t;
   const unsigned e = ((unsigned)__double2hiint(t) >> 20) & 0x7ffu;
-  if (e - 323u >= 1400u) return __ddiv_rn(t, h);  // |t| outside [2^-700, 2^700): subnormal, huge, inf, nan
+  if (e - 323u >= 1400u) {  // |t| outside [2^-700, 2^700): zero (the common case: masked faces), subnormal, huge, inf, nan
+    if (t == 0.0) return h > 0.0 ? t : -t;  // 0 / h is a signed zero
+    return __ddiv_rn(t, h);
+  }
   double q = __dmul_rn(t, rh);
   double r = __fma_rn(-h, q, t);
   q = __fma_rn(r, rh, q);

@@ -270,13 +270,13 @@ __global__ void __launch_bounds__(kSfThreads, 2) div_flux_kernel(
 static constexpr int kBfConsumers = 256;              // 8 consumer warps, 4 columns per thread
 static constexpr int kBfThreads = kBfConsumers;       // thread 0 doubles as the producer (a ninth warp would cap the kernel at 96 registers)
 static constexpr int kBfCW = 4 * kBfConsumers;        // columns per x-chunk
-static constexpr int kBfMaxRows = 128;                // rows per CTA sweep (bounds the flux row slots)
+static constexpr int kBfMaxRows = 64;                 // rows per CTA sweep (bounds the flux row slots)
 
 template <typename Tf> struct BfLayout {
   static constexpr int kFRow = (kBfCW + 8) * (int)sizeof(Tf);  // field row with a 4-column halo on both sides
   static constexpr int kMRow = kBfCW + 16;                     // mask row with a 16-byte halo on the right
   static constexpr int kStage = 5 * kFRow + 2 * kMRow;
-  static constexpr int kStages = sizeof(Tf) == 4 ? 3 : 2;
+  static constexpr int kStages = sizeof(Tf) == 4 ? 4 : 2;
   static constexpr int kRing = kStages * kStage;
 };
 
@@ -299,9 +299,18 @@ struct Recip3 { double x, y, z; };
 
 // face sum S = a + b across an open face, 0 across a closed one (`open` = the mask byte, still in place in its word)
 __device__ __forceinline__ double face_if(double a, double b, uint32_t open) {
-  const double s = __dadd_rn(a, b);
-  return open != 0u ? s : 0.0;
+  double s;  // zero, then a predicated add: one instruction less than add + two 32-bit selects
+  asm("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\nmov.f64 %0, 0d0000000000000000;\n@p add.rn.f64 %0, %1, %2;\n}"
+      : "=d"(s) : "d"(a), "d"(b), "r"(open));
+  return s;
 }
+
+// |d| as float64 for fluid voxels, 0 for solid ones; float32: the select is one AND on the bits before the conversion
+__device__ __forceinline__ double abs_if(float d, uint32_t open) {
+  const uint32_t keep = open != 0u ? 0x7fffffffu : 0u;
+  return (double)__uint_as_float(__float_as_uint(d) & keep);
+}
+__device__ __forceinline__ double abs_if(double d, uint32_t open) { return open != 0u ? fabs(d) : 0.0; }
 
 // Sum over the warp's 128 columns of up to 8 rows at once: every row the lanes park their 4-column sums in
 // vs[row & 7][lane]; here lane = (row, quarter) adds 8 of them (stride 36 doubles: conflict-free both ways) and
@@ -382,21 +391,19 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
     const uint32_t fb = (uint32_t)cw * sizeof(Tf);
     const uint32_t ub = (uint32_t)(cw + left + right) * sizeof(Tf);
     const uint32_t mnb = (uint32_t)cw + (right ? 16u : 0u);
-    const uint32_t total = ub + fb + (y_hi ? 0u : fb + mnb) + (z_lo_edge ? 0u : fb) + (z_hi_edge ? 0u : fb + (uint32_t)cw);
+    // a Neumann edge is the open face between a value and itself (a + a): at the domain edges the neighbour slot
+    // is filled with the row itself, so the consumers have no edge cases in their data path
+    const uint32_t total = ub + 4u * fb + (y_hi ? 0u : mnb) + (z_hi_edge ? 0u : (uint32_t)cw);
     const uint32_t bar = smem_addr(&full_bar[s]);
     const uint32_t sb = smem_addr(ring + (size_t)s * L::kStage);
     mbar_expect_tx(bar, total);
     bulk_g2s(sb + (uint32_t)(4 - left) * sizeof(Tf), u + o0 + o - left, ub, bar);
     bulk_g2s(sb + L::kFRow, w + o0 + o, fb, bar);
-    if (!y_hi) {
-      bulk_g2s(sb + 2 * L::kFRow, v + o0 + o + nx, fb, bar);
-      bulk_g2s(sb + 5 * L::kFRow, mask + o0 + o + nx, mnb, bar);
-    }
-    if (!z_lo_edge) bulk_g2s(sb + 3 * L::kFRow, wb0 + o, fb, bar);
-    if (!z_hi_edge) {
-      bulk_g2s(sb + 4 * L::kFRow, wa0 + o, fb, bar);
-      bulk_g2s(sb + 5 * L::kFRow + L::kMRow, ma0 + o, (uint32_t)cw, bar);
-    }
+    bulk_g2s(sb + 2 * L::kFRow, v + o0 + o + (y_hi ? 0 : nx), fb, bar);
+    if (!y_hi) bulk_g2s(sb + 5 * L::kFRow, mask + o0 + o + nx, mnb, bar);
+    bulk_g2s(sb + 3 * L::kFRow, z_lo_edge ? w + o0 + o : wb0 + o, fb, bar);
+    bulk_g2s(sb + 4 * L::kFRow, z_hi_edge ? w + o0 + o : wa0 + o, fb, bar);
+    if (!z_hi_edge) bulk_g2s(sb + 5 * L::kFRow + L::kMRow, ma0 + o, (uint32_t)cw, bar);
   };
   if (t == 0)
     for (int itp = 0; itp < L::kStages - 1 && itp < total_it; ++itp) produce(itp);
@@ -428,6 +435,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
         for (int j = 0; j < 4; ++j) yface[j] = __dadd_rn(vc[j], vc[j]);  // Neumann edge: F- = v
       }
     }
+#pragma unroll 1  // two rows per trip were tried: 40 % slower (the loop no longer fits the instruction cache)
     for (int y = y0; y < y1; ++y, ++it) {
       {
         const int itp = it + L::kStages - 1;
@@ -458,8 +466,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
       if (lane == 0) mbar_arrive(smem_addr(&empty_bar[s]));  // the stage's values are in registers
       double vsum = 0.0;
       if (in) {
-        // edges as data: a Neumann face is the open face between a value and itself (a + a), so the edge tests
-        // become selects on the neighbour / the mask word instead of per-thread branches
+        // edges as data (see the producer): only the open/closed words depend on the edge flags
         const uint32_t oy = y_hi ? 0xffffffffu : m_next;
         const uint32_t ozl = z_lo_edge ? 0xffffffffu : m_cur;
         const uint32_t ozh = z_hi_edge ? 0xffffffffu : m_above;
@@ -468,13 +475,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
         for (int j = 0; j < 4; ++j) {
           ud[j] = (double)u4.v[j];
           wd[j] = (double)w4.v[j];
-        }
-        if (y_hi) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) vnd[j] = vc[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) vnd[j] = (double)vn4.v[j];
+          vnd[j] = (double)vn4.v[j];
         }
         double xf[5];
         xf[0] = face_if((double)(x_first ? u4.v[0] : u_l), ud[0], x_first ? 1u : (m_cur & 0xffu));
@@ -486,8 +487,8 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
         for (int j = 0; j < 4; ++j) {
           const uint32_t bj = 0xffu << (8 * j);
           const double yn = face_if(vc[j], vnd[j], oy & bj);
-          const double zl = face_if(z_lo_edge ? wd[j] : (double)wb4.v[j], wd[j], ozl & bj);
-          const double zh = face_if(wd[j], z_hi_edge ? wd[j] : (double)wa4.v[j], ozh & bj);
+          const double zl = face_if((double)wb4.v[j], wd[j], ozl & bj);
+          const double zh = face_if(wd[j], (double)wa4.v[j], ozh & bj);
           double ax = __dsub_rn(xf[j + 1], xf[j]);
           double ay = __dsub_rn(yn, yface[j]);
           double az = __dsub_rn(zh, zl);
@@ -498,8 +499,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
           }
           const double d = __dmul_rn(__dadd_rn(__dadd_rn(ax, ay), az), 0.5);
           d4.v[j] = (Tf)d;
-          const Tf da = d4.v[j] < (Tf)0 ? -d4.v[j] : d4.v[j];
-          acc_abs += (double)((m_cur & bj) != 0u ? da : (Tf)0);
+          acc_abs += abs_if(d4.v[j], m_cur & bj);
           col_u[j] += ud[j];
           acc_w += wd[j];
           yface[j] = yn;
@@ -585,7 +585,6 @@ static int launch_div_flux(const void* u, const void* v, const void* w, const ui
   if (bulk) {
     using L = BfLayout<Tf>;
     while (rows > kBfMaxRows) { chunks_y *= 2; rows = (ny + chunks_y - 1) / chunks_y; }
-    if (tuning().stencil_rows > 0) rows = min(kBfMaxRows, tuning().stencil_rows);
     chunks_y = (ny + rows - 1) / rows;
     const size_t smem_b = (size_t)L::kRing + ((size_t)rows + 8 * kBfVsStride) * (kBfConsumers / 32) * sizeof(double);
     const unsigned grid_b = (unsigned)((int64_t)nz * chunks_y);
