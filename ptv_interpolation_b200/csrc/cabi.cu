@@ -61,6 +61,7 @@ extern "C" int ptv_set_tuning(const char* key, double value) {
   else if (!strcmp(key, "linear_k")) { if (!(value >= 4 && value <= 4096)) { set_error("linear_k must be in [4, 4096]"); return PTV_ERR_INVALID; } t.linear_k = (int)value; }
   else if (!strcmp(key, "rscale")) { if (!(value >= 1.0 && value <= 4.0)) { set_error("rscale must be in [1, 4]"); return PTV_ERR_INVALID; } t.rscale = value; }
   else if (!strcmp(key, "stencil_bulk")) t.stencil_bulk = (int)value;
+  else if (!strcmp(key, "rbf_regs")) t.rbf_regs = (int)value;
   else { set_error(std::string("ptv_set_tuning: unknown key ") + key); return PTV_ERR_INVALID; }
   return PTV_OK;
 }
@@ -79,6 +80,7 @@ extern "C" double ptv_get_tuning(const char* key) {
   if (!strcmp(key, "linear_k")) return t.linear_k;
   if (!strcmp(key, "rscale")) return t.rscale;
   if (!strcmp(key, "stencil_bulk")) return t.stencil_bulk;
+  if (!strcmp(key, "rbf_regs")) return t.rbf_regs;
   return nan("");
 }
 

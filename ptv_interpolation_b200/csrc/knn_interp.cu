@@ -51,8 +51,8 @@ __device__ __forceinline__ void sift_down(double* __restrict__ hk, int* __restri
 // conflict free), Gaussian elimination with partial pivoting (the system is symmetric indefinite,
 // so no Cholesky; scipy uses LAPACK dsysv), then vec(x) . c with vec = [phi(|x-y_j|), 1, xh, yh, zh].
 // RPL = matrix rows per lane: 1 for k + 4 <= 32, 2 for k + 4 <= 64.
-__host__ __device__ constexpr int rbf_scratch_doubles(int rpl) {
-  return (32 * rpl) * (32 * rpl + 1) + (32 * rpl) * 3 * 2 + (32 * rpl) / 2;
+__host__ __device__ constexpr int rbf_scratch_doubles(int rpl) {  // rpl 3: the register-resident variant below
+  return rpl >= 3 ? 32 * 13 + 16 : (32 * rpl) * (32 * rpl + 1) + (32 * rpl) * 3 * 2 + (32 * rpl) / 2;
 }
 
 // Scale-invariant kernels of scipy.interpolate.RBFInterpolator (the only ones the reference can reach:
@@ -275,6 +275,174 @@ __device__ void rbf_tps_epilogue(const KnnParams& p, double* __restrict__ scratc
   }
 }
 
+// Register-resident variant for k + tail <= NR <= 32 (kRbf = 3): lane r keeps row r of the system in registers
+// (NR doubles + 3 right-hand sides) and the elimination is shuffles and FMAs only -- no shared-memory matrix, and
+// 3.4 KB of scratch per warp instead of 9 KB.  Registers cannot be indexed at run time and straight-line code for
+// every column (tried first: 45k instructions, 1.7x SLOWER -- a dozen warps stream 100 KB of code per voxel
+// through the instruction cache) is out, so the row ROTATES: every step works on column 0 and writes column j
+// to j - 1, which makes the step one small loop body.  Rotation rules out back substitution (a frozen pivot row
+// would have to be read at a lane-dependent offset), hence Gauss-Jordan: every row but the pivot row is
+// eliminated in every step, the pivot rows end with their pivot alone and x = b / pivot.  Partial pivoting as
+// above (largest |a|, ties to the lowest row).  Scratch per warp: Y[32][3] coordinates, P[32][10] monomials.
+__device__ __noinline__ double rbf_phi_call(int kern, double d2) { return rbf_phi_from_d2(kern, d2); }
+
+template <int T, int NR>
+__device__ __noinline__ void rbf_reg_epilogue(const KnnParams& p, double* __restrict__ scratch, const double* hkey_all,
+                                              const int* hidx_all, double qx, double qy, double qz, bool active,
+                                              double& su, double& sv, double& sw) {
+  static_assert(NR % 4 == 0 && NR <= 32, "rows are built four columns per trip");
+  const unsigned full = 0xffffffffu;
+  const int t = threadIdx.x, lane = t & 31, wbase = t & ~31;
+  const int k = p.k, npoly = p.rbf_npoly, n = k + npoly, kern = p.rbf_kernel;
+  double* Y = scratch;     // [32][3]
+  double* P = Y + 32 * 3;  // [32][10] monomials of the neighbours (scaled coordinates)
+  const HashGrid& g = p.g;
+  double ru = 0.0, rv = 0.0, rw = 0.0;
+#pragma unroll 1
+  for (int v = 0; v < 32; ++v) {
+    if (!__shfl_sync(full, active ? 1 : 0, v)) continue;
+    const double vx = __shfl_sync(full, qx, v), vy = __shfl_sync(full, qy, v), vz = __shfl_sync(full, qz, v);
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    double yx = 0.0, yy = 0.0, yz = 0.0, d2q = 0.0;
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (lane < k) {
+      const int pj = hidx_all[lane * T + wbase + v];
+      d2q = hkey_all[lane * T + wbase + v];
+      yx = g.pts[(int64_t)pj * 3 + 0];
+      yy = g.pts[(int64_t)pj * 3 + 1];
+      yz = g.pts[(int64_t)pj * 3 + 2];
+      const Value4 val = g.vals[pj];
+      b0 = val.u; b1 = val.v; b2 = val.w;
+      Y[lane * 3 + 0] = yx; Y[lane * 3 + 1] = yy; Y[lane * 3 + 2] = yz;
+      mn[0] = mx[0] = yx; mn[1] = mx[1] = yy; mn[2] = mx[2] = yz;
+    }
+    // shift / scale of the neighbourhood (_rbfinterp_xp.py:186-193)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        mn[c] = fmin(mn[c], __shfl_xor_sync(full, mn[c], o));
+        mx[c] = fmax(mx[c], __shfl_xor_sync(full, mx[c], o));
+      }
+    }
+    double shift[3], scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      shift[c] = (mx[c] + mn[c]) / 2.0;
+      scale[c] = (mx[c] - mn[c]) / 2.0;
+      if (scale[c] == 0.0) scale[c] = 1.0;
+    }
+    if (lane < k) {
+      const double hx = (yx - shift[0]) / scale[0], hy = (yy - shift[1]) / scale[1], hz = (yz - shift[2]) / scale[2];
+      for (int m = 0; m < npoly; ++m) P[lane * 10 + m] = rbf_monomial(m, hx, hy, hz);
+    }
+    __syncwarp();
+    // ---- rows: kernel rows K + sI | P for lanes < k, polynomial rows P^T | 0 for lanes k .. n-1; four columns
+    //      per trip enter at the top of the row while the rest moves down
+    double a[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) a[j] = 0.0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < NR; j0 += 4) {
+      double nv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        double val = 0.0;
+        if (j < k) {  // uniform
+          if (lane < k) {
+            const double dx = yx - Y[j * 3 + 0], dy = yy - Y[j * 3 + 1], dz = yz - Y[j * 3 + 2];
+            val = rbf_phi_call(kern, (dx * dx + dy * dy) + dz * dz) + (j == lane ? p.smoothing : 0.0);
+          } else if (lane < n) {
+            val = P[j * 10 + (lane - k)];
+          }
+        } else if (j < n) {
+          if (lane < k) val = P[lane * 10 + (j - k)];
+        }
+        nv[u] = val;
+      }
+#pragma unroll
+      for (int i = 0; i + 4 < NR; ++i) a[i] = a[i + 4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[NR - 4 + u] = nv[u];
+    }
+    // ---- Gauss-Jordan with partial pivoting on the rotating rows
+    bool used = lane >= n;  // lanes beyond the system never pivot
+    int my_col = -1;
+    double my_piv = 1.0;
+    bool singular = false;
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+      // pivot: largest |a[c]| among the unused rows, ties to the lowest row -- two 32-bit warp maxima on the
+      // halves of the non-negative double (its bit pattern orders like the value), then the lowest candidate
+      const double av = fabs(a[0]);
+      const int hi = used ? -1 : __double2hiint(av);
+      const int mh = __reduce_max_sync(full, hi);
+      const bool c1 = !used && hi == mh;
+      const unsigned lo = c1 ? (unsigned)__double2loint(av) : 0u;
+      const unsigned ml = __reduce_max_sync(full, lo);
+      const unsigned cand = __ballot_sync(full, c1 && lo == ml);
+      const int best = __ffs((int)cand) - 1;
+      const double piv = __shfl_sync(full, a[0], best < 0 ? 0 : best);
+      if (best < 0 || !(fabs(piv) > 0.0)) {  // exact zero (or NaN) pivot column: dsysv info > 0
+        singular = true;
+        break;
+      }
+      // multiplier = a[0] * (1 / piv) like LAPACK's dgetf2 (dscal by the reciprocal); the reciprocal comes from
+      // MUFU.RCP64H and two Newton steps: a short dependent chain instead of the IEEE division sequence
+      double rp;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rp) : "d"(piv));
+      rp = fma(fma(-piv, rp, 1.0), rp, rp);
+      rp = fma(fma(-piv, rp, 1.0), rp, rp);
+      double f = a[0] * rp;
+      if (lane == best) { used = true; my_col = c; my_piv = piv; f = 0.0; }
+      if (2 * c < n || NR < 16) {
+#pragma unroll
+        for (int j = 1; j < NR; ++j) {
+          const double pj = __shfl_sync(full, a[j], best);
+          a[j - 1] = fma(-f, pj, a[j]);
+        }
+        a[NR - 1] = 0.0;
+      } else {  // fewer than n / 2 <= NR / 2 columns are still alive
+#pragma unroll
+        for (int j = 1; j <= NR / 2; ++j) {
+          const double pj = __shfl_sync(full, a[j], best);
+          a[j - 1] = fma(-f, pj, a[j]);
+        }
+      }
+      const double p0 = __shfl_sync(full, b0, best), p1 = __shfl_sync(full, b1, best), p2 = __shfl_sync(full, b2, best);
+      b0 = fma(-f, p0, b0); b1 = fma(-f, p1, b1); b2 = fma(-f, p2, b2);
+    }
+    if (singular) {
+      if (lane == 0) atomicExch(p.err_flag, 1);
+      __syncwarp();
+      continue;
+    }
+    // ---- evaluate vec(x) . coeffs (_rbfinterp_xp.py:213-266): this row pivots unknown my_col, coefficient b / pivot
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+    {
+      const int src = my_col >= 0 && my_col < k ? my_col : lane;
+      const double d2c = __shfl_sync(full, d2q, src);  // squared distance voxel -- neighbour my_col
+      if (my_col >= 0) {
+        double vj;
+        if (my_col < k) vj = rbf_phi_call(kern, d2c);
+        else vj = rbf_monomial(my_col - k, (vx - shift[0]) / scale[0], (vy - shift[1]) / scale[1], (vz - shift[2]) / scale[2]);
+        const double w = vj / my_piv;
+        e0 = w * b0; e1 = w * b1; e2 = w * b2;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      e0 += __shfl_xor_sync(full, e0, o);
+      e1 += __shfl_xor_sync(full, e1, o);
+      e2 += __shfl_xor_sync(full, e2, o);
+    }
+    if (lane == v) { ru = e0; rv = e1; rw = e2; }
+    __syncwarp();
+  }
+  su = ru; sv = rv; sw = rw;
+}
+
 template <int T, int TX, int TY, int TZ, typename OutT, int kRbf>  // kRbf: 0 = no RBF, else matrix rows per lane
 __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, unsigned char* smem_raw) {
   static_assert(TX * TY * TZ == T, "tile shape");
@@ -404,8 +572,12 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
 
   if (kRbf) {
     // every lane of the warp helps to solve each voxel's local system, so no early exits here
-    rbf_tps_epilogue<T, (kRbf > 0 ? kRbf : 1)>(p, rbf_scratch + (size_t)(t >> 5) * rbf_scratch_doubles(kRbf > 0 ? kRbf : 1),
-                                               hkey_all, hidx_all, qx, qy, qz, active && kk == k, su, sv, sw);
+    double* ws = rbf_scratch + (size_t)(t >> 5) * rbf_scratch_doubles(kRbf > 0 ? kRbf : 1);
+    if (kRbf >= 3) {  // register-resident rows: 24 (kRbf 3) or 32 (kRbf 4) columns, one kernel each (register budget)
+      rbf_reg_epilogue<T, (kRbf == 3 ? 24 : 32)>(p, ws, hkey_all, hidx_all, qx, qy, qz, active && kk == k, su, sv, sw);
+    } else {
+      rbf_tps_epilogue<T, (kRbf == 2 ? 2 : 1)>(p, ws, hkey_all, hidx_all, qx, qy, qz, active && kk == k, su, sv, sw);
+    }
   }
 
   if (!valid) return;
@@ -556,7 +728,7 @@ __device__ __forceinline__ void heap_tile(const KnnParams& p, const int tile, un
 // One CTA per tile, or -- when the streaming kernel handed over a fail list -- a fixed grid of CTAs
 // striding over the listed tiles.
 template <int T, int TX, int TY, int TZ, typename OutT, int kRbf>
-__global__ void __launch_bounds__(T, 2) knn_interp_kernel(const KnnParams p) {
+__global__ void __launch_bounds__(T, (kRbf == 3 ? 3 : 2)) knn_interp_kernel(const KnnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (p.tile_list == nullptr) {
     heap_tile<T, TX, TY, TZ, OutT, kRbf>(p, (int)blockIdx.x, smem_raw);
@@ -576,7 +748,7 @@ size_t knn_heap_smem_bytes(int T, int k, int method) {
              (size_t)6 * NW * sizeof(double) + (size_t)k * T * sizeof(int) +
              (size_t)(2 * T + 1 + NW) * sizeof(int);
   b = (b + 15) & ~(size_t)15;
-  if (method == PTV_METHOD_RBF) b += 16 + (size_t)NW * rbf_scratch_doubles(k + 10 <= 32 ? 1 : 2) * sizeof(double);  // sized for the largest tail
+  if (method == PTV_METHOD_RBF) b += 16 + (size_t)NW * rbf_scratch_doubles(k + 10 <= 32 ? (tuning().rbf_regs != 0 ? 3 : 1) : 2) * sizeof(double);  // sized for the largest tail
   return (b + 15) & ~(size_t)15;
 }
 
@@ -604,6 +776,10 @@ static int launch_knn(KnnParams& p, cudaStream_t stream) {
 
 int launch_knn_heap(KnnParams& p, int T, bool f32, cudaStream_t stream) {
   if (p.method == PTV_METHOD_RBF) {
+    if (p.k + p.rbf_npoly <= 24 && tuning().rbf_regs != 0)  // register-resident solve
+      return f32 ? launch_knn<128, 8, 4, 4, float, 3>(p, stream) : launch_knn<128, 8, 4, 4, double, 3>(p, stream);
+    if (p.k + p.rbf_npoly <= 32 && tuning().rbf_regs != 0)
+      return f32 ? launch_knn<128, 8, 4, 4, float, 4>(p, stream) : launch_knn<128, 8, 4, 4, double, 4>(p, stream);
     if (p.k + p.rbf_npoly <= 32)
       return f32 ? launch_knn<128, 8, 4, 4, float, 1>(p, stream) : launch_knn<128, 8, 4, 4, double, 1>(p, stream);
     // up to 60 neighbours: two matrix rows per lane, 64-voxel tiles so the 64x65 systems fit in shared memory

@@ -425,6 +425,30 @@ def test_rbf_reference_own_test(golden_dir):
     _assert_vel(np.stack([U, V, W]), g["uvw"], vals)
 
 
+@pytest.mark.parametrize("k,kernel", [(20, "thin_plate_spline"), (26, "thin_plate_spline"), (28, "cubic"), (14, "quintic"),
+                                      (22, "quintic")])
+def test_rbf_register_solver_vs_oracle_and_shared_memory_solver(k, kernel):
+    """k + tail <= 24 and <= 32 take the two register-resident kernels (rotating Gauss-Jordan); both against SciPy
+    (interpolator.py:157-195 -> RBFInterpolator(neighbors=k)) and against the shared-memory elimination."""
+    rng = np.random.default_rng(100 + k)
+    pts = rng.uniform(0.0, 16.0, size=(900, 3))
+    vals = np.stack([np.sin(pts[:, 0] / 3.0), np.cos(pts[:, 1] / 4.0) * pts[:, 2] / 16.0, pts[:, 0] * pts[:, 1] / 200.0], axis=1)
+    b = ((1, 15), (1, 15), (1, 15))
+    grid, _ = gi.create_grid(b, (9, 8, 7))
+    kw = dict(method="rbf", rbf_neighbors=k, rbf_kernel=kernel, out_dtype=np.float64)
+    res = np.stack(gi.interpolate_field(_df(pts, vals), grid, **kw))
+    og, _ = rp.create_grid(b, (9, 8, 7))
+    ref = np.stack(rp.interpolate_field(pts, vals, og, method="rbf", rbf_neighbors=k, rbf_kernel=kernel))
+    scale = np.abs(ref).max()
+    assert np.abs(res - ref).max() <= 1e-9 * scale
+    set_tuning(rbf_regs=0)
+    try:
+        old = np.stack(gi.interpolate_field(_df(pts, vals), grid, **kw))
+    finally:
+        set_tuning(rbf_regs=1)
+    assert np.abs(res - old).max() <= 1e-9 * scale
+
+
 def test_rbf_sphere_pack_vs_oracle_and_errors():
     n = 24
     mask = synthetic.hex6_sphere_pack_mask(n)
