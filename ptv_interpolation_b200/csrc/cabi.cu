@@ -62,6 +62,7 @@ extern "C" int ptv_set_tuning(const char* key, double value) {
   else if (!strcmp(key, "rscale")) { if (!(value >= 1.0 && value <= 4.0)) { set_error("rscale must be in [1, 4]"); return PTV_ERR_INVALID; } t.rscale = value; }
   else if (!strcmp(key, "stencil_bulk")) t.stencil_bulk = (int)value;
   else if (!strcmp(key, "rbf_regs")) t.rbf_regs = (int)value;
+  else if (!strcmp(key, "stencil_la")) t.stencil_la = (int)value;
   else { set_error(std::string("ptv_set_tuning: unknown key ") + key); return PTV_ERR_INVALID; }
   return PTV_OK;
 }

@@ -5,7 +5,6 @@
 #include <math.h>
 
 #include "ptv_internal.cuh"
-#include "bulk_pipe.cuh"
 
 namespace ptv {
 
@@ -328,7 +327,6 @@ __global__ void __launch_bounds__(256) divergence_kernel(
 struct Divisor {
   double den, inv;
   bool pow2;
-  bool fast;  // den inside div_by_spacing's range: reciprocal + two exact FMA corrections instead of the IEEE sequence
 };
 __host__ __device__ inline Divisor make_divisor(double den) {
   Divisor d;
@@ -337,14 +335,10 @@ __host__ __device__ inline Divisor make_divisor(double den) {
   int e;
   const double m = frexp(fabs(den), &e);
   d.pow2 = (m == 0.5) && e > -1000 && e < 1000;
-  d.fast = den == den && fabs(den) > 0x1p-300 && fabs(den) < 0x1p300;
   return d;
 }
 __device__ __forceinline__ double grad_div(double num, const Divisor& d) {
   if (d.pow2) return __dmul_rn(num, d.inv);
-#ifdef __CUDA_ARCH__
-  if (d.fast) return div_by_spacing(num, d.den, d.inv);
-#endif
   if (num == 0.0) return d.den > 0.0 ? num : -num;  // signed zero without the division slow path
   return __ddiv_rn(num, d.den);
 }

@@ -53,6 +53,7 @@ struct Tuning {
   int hull = 2;      // method='linear': hull membership decided on the hull-candidate list (2: cell + particle dominance, 1: cell dominance only), 0 = scan all particles
   double rscale = 1.3;  // stream kernel: first scan radius^2 = rscale * r_est^2
   int rbf_regs = 1;      // local RBF with k + tail <= 32: 1 = register-resident elimination, 0 = shared-memory matrix
+  int stencil_la = 0;    // bulk stencil kernel: rows requested ahead (0 = stages - 2)
   int stencil_bulk = 1;  // stencil kernels: 1 = bulk-async (TMA) row pipelines where shape and alignment allow, 0 = direct loads
 };
 Tuning& tuning();

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
     int nx, int ny, int nz, double dx, double dy, double dz, const Recip3 rh, const Tf* __restrict__ w_below,
     const Tf* __restrict__ w_above, const uint8_t* __restrict__ mask_above, Tf* __restrict__ div,
     double* __restrict__ stats, double* __restrict__ qxy, double* __restrict__ qxz, double* __restrict__ qyz,
-    int rows, int chunks_y) {
+    int rows, int chunks_y, int la) {
   using L = BfLayout<Tf>;
   constexpr int kWarps = kBfConsumers / 32;
   extern __shared__ __align__(128) unsigned char bf_smem[];
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
   int acc_cnt = 0;
   const int64_t o0 = (int64_t)z * plane + (int64_t)y0 * nx;  // first row of the sweep
 
-  // ---------------- producer duty: row `itp` is requested by lane 0 of warp itp % 8, kStages - 1 rows ahead of
+  // ---------------- producer duty: row `itp` is requested by lane 0 of warp itp % 8, `la` rows ahead of
   // its use (rotating the duty keeps the warps level: a warp that always produced would trail the others, and
   // they would burn its issue slots polling the barrier it has not armed yet)
   const Tf* wb0 = z > 0 ? w + o0 - plane : (w_below != nullptr ? w_below + (int64_t)y0 * nx : nullptr);
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
     if (!z_hi_edge) bulk_g2s(sb + 5 * L::kFRow + L::kMRow, ma0 + o, (uint32_t)cw, bar);
   };
   if (t == 0)
-    for (int itp = 0; itp < L::kStages - 1 && itp < total_it; ++itp) produce(itp);
+    for (int itp = 0; itp < la && itp < total_it; ++itp) produce(itp);
 
   // ---------------- consumers
   double* vs = vs_all + warp * 8 * kBfVsStride;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) div_flux_bulk_kernel(
 #pragma unroll 1  // two rows per trip were tried: 40 % slower (the loop no longer fits the instruction cache)
     for (int y = y0; y < y1; ++y, ++it) {
       {
-        const int itp = it + L::kStages - 1;
+        const int itp = it + la;
         if (lane == 0 && (itp & (kWarps - 1)) == warp && itp < total_it) produce(itp);
       }
       const int s = it % L::kStages;
@@ -588,6 +588,10 @@ static int launch_div_flux(const void* u, const void* v, const void* w, const ui
     chunks_y = (ny + rows - 1) / rows;
     const size_t smem_b = (size_t)L::kRing + ((size_t)rows + 8 * kBfVsStride) * (kBfConsumers / 32) * sizeof(double);
     const unsigned grid_b = (unsigned)((int64_t)nz * chunks_y);
+    // rows requested ahead of their use: one less than the ring could hold, so that the warp on producer duty finds
+    // the stage it refills released two rows ago -- with stages - 1 it waits for the slowest warp of the CTA every
+    // row and the others queue up behind it (1024^3: 4.5 ms; with the slack: 3.35 ms)
+    const int la = max(1, min(L::kStages - 1, tuning().stencil_la > 0 ? tuning().stencil_la : L::kStages - 2));
     Recip3 rh;
     rh.x = 1.0 / dx; rh.y = 1.0 / dy; rh.z = 1.0 / dz;
 #define PTV_BF_LAUNCH(UNIT)                                                                                       \
@@ -596,7 +600,7 @@ static int launch_div_flux(const void* u, const void* v, const void* w, const ui
     PTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));               \
     kern<<<grid_b, kBfThreads, smem_b, s>>>((const Tf*)u, (const Tf*)v, (const Tf*)w, mask, nx, ny, nz, dx, dy,   \
                                             dz, rh, (const Tf*)w_below, (const Tf*)w_above, mask_above, (Tf*)div, \
-                                            stats, qxy, qxz, qyz, rows, chunks_y);                                \
+                                            stats, qxy, qxz, qyz, rows, chunks_y, la);                            \
   } while (0)
     if (unit) PTV_BF_LAUNCH(true); else PTV_BF_LAUNCH(false);
 #undef PTV_BF_LAUNCH
