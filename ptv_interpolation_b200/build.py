@@ -21,7 +21,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libptvb200.so")
 STAMP = LIB + ".stamp"
 SOURCES = ["cabi.cu", "hash_build.cu", "knn_interp.cu", "knn_stream.cu", "knn_duo.cu", "knn_dispatch.cu",
-           "delaunay_linear.cu", "grid_ops.cu", "stencil_fused.cu", "projection.cu"]
+           "delaunay_linear.cu", "grid_ops.cu", "stencil_fused.cu", "strain_bulk.cu", "projection.cu"]
 HEADERS = [os.path.join(CSRC, "ptv_internal.cuh"), os.path.join(CSRC, "knn_common.cuh"), os.path.join(CSRC, "bulk_pipe.cuh"), os.path.join(ROOT, "include", "ptv_b200.h")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -8,6 +8,9 @@
 
 namespace ptv {
 
+int launch_strain_vorticity_bulk(const float* u, const float* v, const float* w, const uint8_t* mask, int nx, int ny,
+                                 int nz, double dx, double dy, double dz, float* strain, float* vort, cudaStream_t s);
+
 // ------------------------------------------------------------------ mask gather (a2)
 // out[z,y,x] = raw[iz[z], iy[y], ix[x]] != 0, 0 where any index is -1 (out of bounds ->
 // fill_value 0, interpolator.py:230-231).  A warp owns 512 consecutive x of one output row: lane l handles
@@ -554,6 +557,11 @@ extern "C" int ptv_strain_vorticity(const void* d_u, const void* d_v, const void
     // np.gradient: "Shape of array too small to calculate a numerical gradient, at least 2 elements are required"
     set_error("Shape of array too small to calculate a numerical gradient, at least (edge_order + 1) elements are required.");
     return PTV_ERR_INVALID;
+  }
+  if (dtype == PTV_F32) {  // z-marching kernel over bulk-copied plane tiles (strain_bulk.cu) where shape and alignment allow
+    const int rc = launch_strain_vorticity_bulk((const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dx,
+                                                dy, dz, (float*)d_strain, (float*)d_vorticity, (cudaStream_t)stream);
+    if (rc != -1) return rc;
   }
   const int64_t n = (int64_t)nx * ny * nz;
   const unsigned nb = (unsigned)((n + 255) / 256);

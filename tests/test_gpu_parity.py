@@ -781,6 +781,35 @@ def test_strain_vorticity_golden(golden_dir):
         assert np.array_equal(gva.compute_vorticity(uf, vf, wf, *h, mask=m), ref.astype(np.float32))
 
 
+@pytest.mark.parametrize("shape,h", [((40, 19, 144), (1.0, 1.0, 1.0)), ((70, 9, 32), (0.5, 2.0, 4.0)),
+                                     ((33, 8, 256), (2.00625, 2.00625, 2.00625)), ((3, 3, 16), (1.0, 1.0, 1.0)),
+                                     ((66, 17, 128), (1.25, 0.75, 2.0))])
+def test_strain_vorticity_bulk_kernel(shape, h):
+    """float32 fields with nx % 16 == 0 take the z-marching kernel over bulk-copied plane tiles (strain_bulk.cu):
+    several x / y tiles, ragged tiles, z cut into segments, one-sided differences at all six faces; against the
+    oracle on the upcast field (velocity_analysis.py:10-63, 94-120) and against the direct-load kernel."""
+    from ptv_interpolation_b200 import velocity_analysis as gva
+    rng = np.random.default_rng(shape[2] + shape[0])
+    u, v, w = (rng.normal(size=shape).astype(np.float32) for _ in range(3))
+    m = rng.random(shape) > 0.4
+    m[:, :, : shape[2] // 3] &= rng.random() > 0.5  # a solid (or untouched) slab: whole warps without work
+    u64, v64, w64 = (a.astype(np.float64) for a in (u, v, w))
+    for mm in (m, None):
+        s_ref = rp.compute_strain_rate(u64, v64, w64, *h, mask=mm).astype(np.float32)
+        o_ref = rp.compute_vorticity(u64, v64, w64, *h, mask=mm).astype(np.float32)
+        assert np.array_equal(gva.compute_strain_rate(u, v, w, *h, mask=mm), s_ref)
+        assert np.array_equal(gva.compute_vorticity(u, v, w, *h, mask=mm), o_ref)
+    eng = PTVEngine()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    s1, o1 = eng.strain_vorticity(t(u), t(v), t(w), *h, mask=t(m))
+    set_tuning(stencil_bulk=0)
+    try:
+        s0, o0 = eng.strain_vorticity(t(u), t(v), t(w), *h, mask=t(m))
+    finally:
+        set_tuning(stencil_bulk=1)
+    assert torch.equal(s0, s1) and torch.equal(o0, o1)
+
+
 # ------------------------------------------------------------------ N2: projection cleaning
 def test_projection_cleaning_golden(golden_dir, capsys):
     g = np.load(os.path.join(golden_dir, "case_h_projection.npz"))
