@@ -2,12 +2,10 @@
 // z-MARCHING kernel over shared-memory plane tiles filled by 1-D bulk copies (cp.async.bulk, the TMA engine).
 //
 // The nine np.gradient stencils of a voxel read 6 neighbours of each of u, v, w.  A CTA owns a column of 8 rows x
-// 128 x-positions and walks up in z: a warp owns one row, a lane four consecutive x.  The z-neighbours of a voxel
-// are the thread's own values of the planes before and after (registers), its x / y neighbours come from the
-// current plane's tile in shared memory ((8 + 2) rows x (128 + 8) columns per field, halo included), so a field
-// value crosses L2 -> SM 1.33 times instead of five (y-marching: three; one load per neighbour: seven).  The tiles
-// travel through a ring of six stages three planes ahead of their use; a stage is read at two consecutive
-// steps (first the thread's own values, as the "plane after", then the neighbours, as the centre plane).
+// 128 x-positions and walks up in z; a warp owns one row.  Three consecutive plane tiles ((8 + 2) rows x (128 + 8)
+// columns per field, halo included) are resident in shared memory: the centre plane and its z-neighbours, so a
+// field value crosses L2 -> SM 1.33 times instead of seven (one load per neighbour) and every neighbour of a voxel is
+// one shared-memory read.  The tiles travel through a ring of six stages two planes ahead of their use.
 // Arithmetic, operation order and divisions are those of the direct-load kernels in grid_ops.cu (bit-identical
 // float64 results, rounded to float32 once).
 #include <math.h>
@@ -38,6 +36,7 @@ static constexpr int kSbFRows = kSbRows + 2; // staged rows per field (one halo 
 static constexpr int kSbStages = 6;         // 2 CTAs x 6 x 17 KB; a stage is held for two steps
 static constexpr int kSbFieldBytes = kSbFRows * kSbFRow * 4;                         // 5440
 static constexpr int kSbStageBytes = ((3 * kSbFieldBytes + kSbRows * kSbCols) + 127) / 128 * 128;  // + mask tile
+static constexpr int kSbWarpBytes = 2 * kSbCols * 4 + kSbCols;  // per warp: two result rows and the fluid-voxel list
 
 template <bool kPow2>
 __global__ void __launch_bounds__(kSbThreads, 2) strain_vorticity_bulk_kernel(
@@ -103,18 +102,25 @@ __global__ void __launch_bounds__(kSbThreads, 2) strain_vorticity_bulk_kernel(
   for (int k = 0; k < la && k < nsteps; ++k)
     if (warp == (k & (kSbRows - 1))) produce(k);
 
-  // ---------------- consumers
+  // ---------------- consumers.  Step k: plane zs - 1 + k has arrived; the centre plane is the one before it, its
+  // z-neighbours sit in the stages before and after.  Only FLUID voxels cost arithmetic (velocity_analysis.py:58-61,
+  // 116-117 zero the solid ones), and in a porous medium a warp's 128 voxels are a patchwork of both -- so the warp
+  // compacts the fluid voxels of its row into a list and lane i takes list entries i, i + 32, ...: the ~130
+  // float64 instructions per voxel run with (nearly) all lanes busy instead of the 40 % a fixed voxel-to-lane
+  // mapping gives at porosity 0.4.  Every neighbour is one scalar read of a staged tile (domain edges: the
+  // neighbour index is clamped to the voxel itself, np.gradient's one-sided difference), results go through a
+  // per-warp row buffer so the global stores stay 16-byte vectors.
   const int y = y0 + warp, x = x0 + 4 * lane;
   const bool in = y < ny && x < nx;
-  const bool x_first = x == 0, x_last = x + 4 >= nx, y_first = y == 0, y_last = y == ny - 1;
-  const int own = ((warp + 1) * kSbFRow + 4 + 4 * lane) * 4;  // byte offset of the thread's four values in a field tile
-  float prv[3][4], cen[3][4], nxt[3][4];
-#pragma unroll
-  for (int f = 0; f < 3; ++f)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) prv[f][j] = cen[f][j] = nxt[f][j] = 0.0f;
-  const SbDivisor dxe = dv.d[0], dxi = dv.d[1], dye = dv.d[2], dyi = dv.d[3], dze = dv.d[4], dzi = dv.d[5];
-  const SbDivisor dyy = (y_first || y_last) ? dye : dyi;
+  const bool y_first = y == 0, y_last = y == ny - 1;
+  unsigned char* wsm = sb_smem + (size_t)kSbStages * kSbStageBytes + (size_t)warp * kSbWarpBytes;
+  float* outs = reinterpret_cast<float*>(wsm);            // [128] shear rate of the row
+  float* outv = outs + kSbCols;                           // [128] vorticity
+  uint8_t* list = reinterpret_cast<uint8_t*>(outv + kSbCols);  // [128] x-offsets of the row's fluid voxels
+  const SbDivisor dxe = dv.d[0], dxi = dv.d[1], dze = dv.d[4], dzi = dv.d[5];
+  const SbDivisor dyy = (y_first || y_last) ? dv.d[2] : dv.d[3];
+  const int rowc = (warp + 1) * kSbFRow, rowu = (y_first ? warp + 1 : warp) * kSbFRow, rowd = (y_last ? warp + 1 : warp + 2) * kSbFRow;
+  const unsigned lt = (1u << lane) - 1u;
 
 #pragma unroll 1
   for (int k = 0; k < nsteps; ++k) {
@@ -122,85 +128,71 @@ __global__ void __launch_bounds__(kSbThreads, 2) strain_vorticity_bulk_kernel(
       const int kp = k + la;
       if (kp < nsteps && warp == (kp & (kSbRows - 1))) produce(kp);
     }
-    const int s = k % kSbStages;
-    const unsigned char* sb = sb_smem + (size_t)s * kSbStageBytes;
-    mbar_wait(smem_addr(&full_bar[s]), (k / kSbStages) & 1);
-    const int zp = zs - 1 + k;  // the plane that has just arrived: the "plane after" of the centre plane zp - 1
-    if (in && zp >= 0 && zp < nz) {
+    mbar_wait(smem_addr(&full_bar[k % kSbStages]), (k / kSbStages) & 1);
+    if (k < 2) continue;
+    const int zc = zs + k - 2;  // centre plane
+    const int sa = (k - 2) % kSbStages, sc = (k - 1) % kSbStages, sn = k % kSbStages;
+    const float* tc = reinterpret_cast<const float*>(sb_smem + (size_t)sc * kSbStageBytes);
+    const bool z_first = zc == 0, z_last = zc == nz - 1;
+    const float* tlo = z_first ? tc : reinterpret_cast<const float*>(sb_smem + (size_t)sa * kSbStageBytes);
+    const float* thi = z_last ? tc : reinterpret_cast<const float*>(sb_smem + (size_t)sn * kSbStageBytes);
+    const SbDivisor dzz = (z_first || z_last) ? dze : dzi;
+    // ---- fluid voxels of the row, in x order
+    uint32_t m4 = 0u;
+    if (in) m4 = mask != nullptr ? *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(tc) + 3 * kSbFieldBytes + warp * kSbCols + 4 * lane)
+                                 : 0x01010101u;
+    int total = 0, rank = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool fl = (m4 & (0xffu << (8 * j))) != 0u;
+      const unsigned bal = __ballot_sync(0xffffffffu, fl);
+      // voxels are ordered lane-major (x = 4 lane + j): everything in lower lanes, then this lane's earlier j
+      total += __popc(bal);
+      rank += __popc(bal & lt);
+    }
+    {
+      int r = rank;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((m4 & (0xffu << (8 * j))) != 0u) list[r++] = (uint8_t)(4 * lane + j);
+    }
+    *reinterpret_cast<float4*>(outs + 4 * lane) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    *reinterpret_cast<float4*>(outv + 4 * lane) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < total; i += 32) {
+      const int xo = list[i];
+      const int xg = x0 + xo, cx = 4 + xo;
+      const bool xe0 = xg == 0, xe1 = xg == nx - 1;
+      const int cl = xe0 ? cx : cx - 1, cr = xe1 ? cx : cx + 1;
+      const SbDivisor dxx = (xe0 || xe1) ? dxe : dxi;
+      double gx[3], gy[3], gz[3];
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
-        const float4 q = *reinterpret_cast<const float4*>(sb + f * kSbFieldBytes + own);
-        nxt[f][0] = q.x; nxt[f][1] = q.y; nxt[f][2] = q.z; nxt[f][3] = q.w;
+        const int fo = f * (kSbFieldBytes / 4);
+        gx[f] = sb_div<kPow2>(__dsub_rn((double)tc[fo + rowc + cr], (double)tc[fo + rowc + cl]), dxx);
+        gy[f] = sb_div<kPow2>(__dsub_rn((double)tc[fo + rowd + cx], (double)tc[fo + rowu + cx]), dyy);
+        gz[f] = sb_div<kPow2>(__dsub_rn((double)thi[fo + rowc + cx], (double)tlo[fo + rowc + cx]), dzz);
+      }
+      if (strain != nullptr) {
+        const double exx = __dmul_rn(2.0, gx[0]), eyy = __dmul_rn(2.0, gy[1]), ezz = __dmul_rn(2.0, gz[2]);
+        const double exy = __dadd_rn(gy[0], gx[1]), exz = __dadd_rn(gz[0], gx[2]), eyz = __dadd_rn(gz[1], gy[2]);
+        const double diag = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(exx, exx), __dmul_rn(eyy, eyy)), __dmul_rn(ezz, ezz)));
+        outs[xo] = (float)sqrt(__dadd_rn(__dadd_rn(__dadd_rn(diag, __dmul_rn(exy, exy)), __dmul_rn(exz, exz)), __dmul_rn(eyz, eyz)));
+      }
+      if (vort != nullptr) {
+        const double vx = __dsub_rn(gy[2], gz[1]), vy = __dsub_rn(gz[0], gx[2]), vz = __dsub_rn(gx[1], gy[0]);
+        outv[xo] = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
       }
     }
-    if (k >= 1) {
-      const int sc = (k - 1) % kSbStages;  // the centre plane's tile: neighbours in x and y, mask
-      const unsigned char* sbc = sb_smem + (size_t)sc * kSbStageBytes;
-      const int zc = zp - 1;
-      const bool work = k >= 2 && in;
-      uint32_t m4 = 0x01010101u;
-      float up[3][4], dn[3][4], xl[3], xr[3];
-      if (work) {
-        if (mask != nullptr) m4 = *reinterpret_cast<const uint32_t*>(sbc + 3 * kSbFieldBytes + warp * kSbCols + 4 * lane);
-        if (m4 != 0u) {
-#pragma unroll
-          for (int f = 0; f < 3; ++f) {
-            const unsigned char* ft = sbc + f * kSbFieldBytes;
-            const float4 a = *reinterpret_cast<const float4*>(ft + own - kSbFRow * 4);
-            const float4 c = *reinterpret_cast<const float4*>(ft + own + kSbFRow * 4);
-            up[f][0] = a.x; up[f][1] = a.y; up[f][2] = a.z; up[f][3] = a.w;
-            dn[f][0] = c.x; dn[f][1] = c.y; dn[f][2] = c.z; dn[f][3] = c.w;
-            xl[f] = *reinterpret_cast<const float*>(ft + own - 4);
-            xr[f] = *reinterpret_cast<const float*>(ft + own + 16);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_addr(&empty_bar[sc]));  // the centre tile's values are in registers
-      if (work) {
-        float so[4] = {0.0f, 0.0f, 0.0f, 0.0f}, vo[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (m4 != 0u) {
-          const bool z_first = zc == 0, z_last = zc == nz - 1;
-          const SbDivisor dzz = (z_first || z_last) ? dze : dzi;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if ((m4 & (0xffu << (8 * j))) == 0u) continue;  // solid voxel: 0 (velocity_analysis.py:58-61,116-117)
-            const bool xe = (j == 0 && x_first) || (j == 3 && x_last);
-            const SbDivisor dxx = xe ? dxe : dxi;
-            double gx[3], gy[3], gz[3];
-#pragma unroll
-            for (int f = 0; f < 3; ++f) {
-              const double c = (double)cen[f][j];
-              // np.gradient: central difference over 2 h inside, one-sided over h at the two ends of an axis
-              const double xa = j == 0 ? (x_first ? c : (double)xl[f]) : (double)cen[f][j > 0 ? j - 1 : 0];
-              const double xb = j == 3 ? (x_last ? c : (double)xr[f]) : (double)cen[f][j < 3 ? j + 1 : 3];
-              gx[f] = sb_div<kPow2>(__dsub_rn(xb, xa), dxx);
-              const double ya = y_first ? c : (double)up[f][j], yb = y_last ? c : (double)dn[f][j];
-              gy[f] = sb_div<kPow2>(__dsub_rn(yb, ya), dyy);
-              const double za = z_first ? c : (double)prv[f][j], zb = z_last ? c : (double)nxt[f][j];
-              gz[f] = sb_div<kPow2>(__dsub_rn(zb, za), dzz);
-            }
-            if (strain != nullptr) {
-              const double exx = __dmul_rn(2.0, gx[0]), eyy = __dmul_rn(2.0, gy[1]), ezz = __dmul_rn(2.0, gz[2]);
-              const double exy = __dadd_rn(gy[0], gx[1]), exz = __dadd_rn(gz[0], gx[2]), eyz = __dadd_rn(gz[1], gy[2]);
-              const double diag = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(exx, exx), __dmul_rn(eyy, eyy)), __dmul_rn(ezz, ezz)));
-              so[j] = (float)sqrt(__dadd_rn(__dadd_rn(__dadd_rn(diag, __dmul_rn(exy, exy)), __dmul_rn(exz, exz)), __dmul_rn(eyz, eyz)));
-            }
-            if (vort != nullptr) {
-              const double vx = __dsub_rn(gy[2], gz[1]), vy = __dsub_rn(gz[0], gx[2]), vz = __dsub_rn(gx[1], gy[0]);
-              vo[j] = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
-            }
-          }
-        }
-        const int64_t o = (int64_t)zc * plane + (int64_t)y * nx + x;
-        if (strain != nullptr) *reinterpret_cast<float4*>(strain + o) = make_float4(so[0], so[1], so[2], so[3]);
-        if (vort != nullptr) *reinterpret_cast<float4*>(vort + o) = make_float4(vo[0], vo[1], vo[2], vo[3]);
-      }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_addr(&empty_bar[sa]));  // the plane below the centre is done with
+    if (in) {
+      const int64_t o = (int64_t)zc * plane + (int64_t)y * nx + x;
+      if (strain != nullptr) *reinterpret_cast<float4*>(strain + o) = *reinterpret_cast<const float4*>(outs + 4 * lane);
+      if (vort != nullptr) *reinterpret_cast<float4*>(vort + o) = *reinterpret_cast<const float4*>(outv + 4 * lane);
     }
-#pragma unroll
-    for (int f = 0; f < 3; ++f)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { prv[f][j] = cen[f][j]; cen[f][j] = nxt[f][j]; }
+    __syncwarp();  // the row buffers are rewritten in the next step
   }
 }
 
@@ -234,10 +226,10 @@ int launch_strain_vorticity_bulk(const float* u, const float* v, const float* w,
   zsplit = (nz + zseg - 1) / zseg;
   const int64_t grid = (int64_t)tiles_x * tiles_y * zsplit;
   if (grid > 2147483647LL) return -1;
-  const size_t smem = (size_t)kSbStages * kSbStageBytes;
-  // planes requested ahead: a tile is released one step after its own step, and two more steps of slack keep the
-  // warp on producer duty from waiting for the slowest warp (stencil_fused.cu)
-  const int la = max(1, min(kSbStages - 2, tuning().stencil_la > 0 ? tuning().stencil_la : kSbStages - 3));
+  const size_t smem = (size_t)kSbStages * kSbStageBytes + (size_t)kSbRows * kSbWarpBytes;
+  // planes requested ahead: a tile is held for three steps (plane above, centre, plane below); one more step of
+  // slack keeps the warp on producer duty from waiting for the slowest warp (stencil_fused.cu)
+  const int la = max(1, min(kSbStages - 3, tuning().stencil_la > 0 ? tuning().stencil_la : kSbStages - 4));
 #define PTV_SB_LAUNCH(P2)                                                                                   \
   do {                                                                                                      \
     auto kern = strain_vorticity_bulk_kernel<P2>;                                                           \
