@@ -71,7 +71,10 @@ int ptv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, siz
  * kernel, "stream" 0|1 use the streaming kernel, "stats" 0|1, "rscale" first-radius factor of the
  * streaming kernel; method='linear': "hull" 2|1|0 hull-candidate list with / without the particle-level
  * stage / none (scan all particles), "linear_k" the first candidate radius holds this many particles,
- * "linear_occ" 3|4 CTAs per SM).  Results never depend on them.  Unknown key -> PTV_ERR_INVALID. */
+ * "linear_occ" 3|4 CTAs per SM; "stencil_bulk" 1|0 stencil kernels on bulk-async (TMA) shared-memory rings /
+ * direct loads, "stencil_la" rows or planes requested ahead in those rings (0 = default); "rbf_regs" 1|0
+ * register-resident / shared-memory local-RBF solve).  Results never depend on them.  Unknown key ->
+ * PTV_ERR_INVALID. */
 int ptv_set_tuning(const char* key, double value);
 /* Number of CUDA kernels this library has launched in this process so far (bench.py's
  * gpu_launches is the difference across the timed region). */
