@@ -607,7 +607,7 @@ def run_b200(args):
     st_ms = float(np.mean(phase_ms["stencils"]))
     st_bytes = 17.0 * nzl * n * n  # fused divergence + flux + statistics: 12 B u,v,w + 1 B mask read, 4 B div written
     bd_ms = float(np.mean(phase_ms["build"]))
-    roofline_other = [{"kernel": "div_flux_kernel (1 launch + halo/reduce)", "bound": "hbm",
+    roofline_other = [{"kernel": "div_flux_bulk_kernel (1 launch + halo/reduce)", "bound": "hbm",
                        "achieved": st_bytes / (st_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": st_bytes / (st_ms * 1e-3) / 1e9 / peak, "ms": st_ms},
                       {"kernel": "hash build", "bound": "hbm",

@@ -147,7 +147,7 @@ def test_exact_division_by_spacing():
 # nx % 16 == 0 -> bulk-async row pipeline (one chunk, two chunks with x halos, ragged last chunk, > 256 rows per
 # z-plane so a plane is swept by several CTAs); the other shapes take the direct-load kernels
 @pytest.mark.parametrize("shape", [(11, 9, 7), (6, 10, 16), (5, 33, 1028), (3, 4, 2052), (4, 37, 1040), (6, 5, 2080),
-                                   (7, 300, 48), (2, 3, 1024)])
+                                   (7, 300, 48), (2, 3, 1024), (1, 1, 16), (1, 5, 32), (5, 1, 64), (2, 66, 16)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_fused_divergence_flux(shape, dtype):
     rng = np.random.default_rng(shape[2])
