@@ -20,7 +20,7 @@ import weakref
 import numpy as np
 import torch
 
-_CHUNK_BYTES = 64 << 20
+_CHUNK_BYTES = 32 << 20
 _lock = threading.Lock()
 _pool = None
 
@@ -59,36 +59,55 @@ def _staging_for(dev):
         return _staging[key]
 
 
-def stage_to_device(arr, dev, out=None, stream=None):
-    """Copy a C-contiguous NumPy array to a (new or given) device tensor of the same shape/dtype through
-    the pinned staging chunks; the DMAs run on ``stream`` (default: the current stream).  Returns when the
-    host array has been fully read and the last DMA has completed."""
+def _as_bytes(arr):
     arr = np.ascontiguousarray(arr)
-    h_flat = arr.view(np.uint8).reshape(-1) if arr.dtype == np.bool_ else arr.reshape(-1).view(np.uint8)
-    nbytes = h_flat.shape[0]
-    tdt = torch.from_numpy(np.empty(0, dtype=np.uint8 if arr.dtype == np.bool_ else arr.dtype)).dtype
-    if out is None:
-        out = torch.empty(arr.shape, dtype=tdt, device=dev)
-    dflat = out.reshape(-1).view(torch.uint8)
-    if nbytes == 0:
-        return out
+    flat = arr.view(np.uint8).reshape(-1) if arr.dtype == np.bool_ else arr.reshape(-1).view(np.uint8)
+    return arr, flat
+
+
+def stage_many_to_device(pairs, dev, stream=None):
+    """``pairs``: (C-contiguous NumPy array, device tensor of the same byte size) -- all of them go through the two
+    pinned staging chunks as ONE stream of chunks: the host copy of a chunk overlaps the DMA of the previous one
+    across array boundaries, and the host waits for the DMAs only once, at the end (six particle columns of 80 MB:
+    27 ms one by one, each with its own tail -> about half)."""
     bufs, evs = _staging_for(dev)
     if stream is None:
         stream = torch.cuda.current_stream(dev)
     used = [False, False]
-    for i, off in enumerate(range(0, nbytes, _CHUNK_BYTES)):
-        b = i & 1
-        n = min(_CHUNK_BYTES, nbytes - off)
-        if used[b]:
-            evs[b].synchronize()  # the DMA that last read this chunk has finished
-        _parallel_copy(bufs[b].numpy()[:n], h_flat[off:off + n])  # host -> pinned, a few threads
-        with torch.cuda.stream(stream):
-            dflat[off:off + n].copy_(bufs[b][:n], non_blocking=True)
-        evs[b].record(stream)
-        used[b] = True
+    i = 0
+    for arr, out in pairs:
+        _, h_flat = _as_bytes(arr)
+        nbytes = h_flat.shape[0]
+        dflat = out.reshape(-1).view(torch.uint8)
+        if dflat.numel() != nbytes:
+            raise ValueError("stage_many_to_device: size mismatch")
+        for off in range(0, nbytes, _CHUNK_BYTES):
+            b = i & 1
+            i += 1
+            n = min(_CHUNK_BYTES, nbytes - off)
+            if used[b]:
+                evs[b].synchronize()  # the DMA that last read this chunk has finished
+            _parallel_copy(bufs[b].numpy()[:n], h_flat[off:off + n])  # host -> pinned, a few threads
+            with torch.cuda.stream(stream):
+                dflat[off:off + n].copy_(bufs[b][:n], non_blocking=True)
+            evs[b].record(stream)
+            used[b] = True
     for b in range(2):  # the chunks are shared by later calls on other streams
         if used[b]:
             evs[b].synchronize()
+
+
+def stage_to_device(arr, dev, out=None, stream=None):
+    """Copy a C-contiguous NumPy array to a (new or given) device tensor of the same shape/dtype through
+    the pinned staging chunks; the DMAs run on ``stream`` (default: the current stream).  Returns when the
+    host array has been fully read and the last DMA has completed."""
+    arr, h_flat = _as_bytes(arr)
+    tdt = torch.from_numpy(np.empty(0, dtype=np.uint8 if arr.dtype == np.bool_ else arr.dtype)).dtype
+    if out is None:
+        out = torch.empty(arr.shape, dtype=tdt, device=dev)
+    if h_flat.shape[0] == 0:
+        return out
+    stage_many_to_device([(arr, out)], dev, stream=stream)
     return out
 
 

@@ -121,8 +121,7 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
     # particle table (interpolator.py:78-79): the six columns go to the device one by one through the pinned
     # staging chunks and are interleaved into (Np,3) rows THERE -- df[[...]].values would transpose 2 x 24 B
     # per particle on one host core first
-    pts = _columns_to_device(df, ("x", "y", "z"), dev, shard_inputs)
-    vals = _columns_to_device(df, ("u", "v", "w"), dev, shard_inputs)
+    pts, vals = _tables_to_device(df, dev, shard_inputs)
     npart = pts.shape[0]
     k = {"idw": idw_neighbors, "sibson": sibson_neighbors, "nearest": 1, "rbf": rbf_neighbors, "linear": 4}[method]
     if method == "rbf":
@@ -161,6 +160,22 @@ def interpolate_field(df, grid_tuple, method="linear", rbf_neighbors=20, rbf_ker
 
 
 _dev_results = {}
+
+
+def _tables_to_device(df, dev, shard=False):
+    """(points, values): the two (Np,3) float64 device tensors of interpolator.py:78-79.  One rank: the six columns
+    travel as ONE stream of staging chunks into a (6, Np) device buffer and are interleaved there."""
+    import torch
+    import torch.distributed as dist
+    from . import hostmem
+    world = dist.get_world_size() if (shard and dist.is_available() and dist.is_initialized()) else 1
+    if world > 1:
+        return _columns_to_device(df, ("x", "y", "z"), dev, True), _columns_to_device(df, ("u", "v", "w"), dev, True)
+    n = len(df)
+    cols = [np.ascontiguousarray(df[c].to_numpy(dtype=np.float64, copy=False)) for c in ("x", "y", "z", "u", "v", "w")]
+    tmp = torch.empty((6, n), dtype=torch.float64, device=dev)
+    hostmem.stage_many_to_device([(col, tmp[j]) for j, col in enumerate(cols)], dev)
+    return tmp[:3].t().contiguous(), tmp[3:].t().contiguous()
 
 
 def _columns_to_device(df, cols, dev, shard=False):
