@@ -31,19 +31,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 // t / h, correctly rounded, from rh = RN(1 / h): two Newton corrections with exact FMA residuals.  After the
 // first one q is a faithful quotient, and for a faithful q the second one returns RN(t / h) (Markstein 1990).
-// Needs t, h and t / h well inside the normal range (checked: by the caller for h, here for t); everything
-// else takes the IEEE division.  ptv_selftest_division compares it with __ddiv_rn on the device.
+// Needs t, h and t / h well inside the normal range (checked: by the caller for h, here for t).  Zero numerators
+// (masked faces: the common case) stay on the straight-line path -- the sequence yields a zero, only its sign is
+// set afterwards -- and the rest (subnormal, huge, inf, nan) takes the IEEE division out of line, so the loop
+// bodies that divide stay small.  ptv_selftest_division compares it with __ddiv_rn on the device.
+static __device__ __noinline__ double div_by_spacing_slow(double t, double h) { return __ddiv_rn(t, h); }
+
 __device__ __forceinline__ double div_by_spacing(double t, double h, double rh) {
-  const unsigned e = ((unsigned)__double2hiint(t) >> 20) & 0x7ffu;
-  if (e - 323u >= 1400u) {  // |t| outside [2^-700, 2^700): zero (the common case: masked faces), subnormal, huge, inf, nan
-    if (t == 0.0) return h > 0.0 ? t : -t;  // 0 / h is a signed zero
-    return __ddiv_rn(t, h);
-  }
   double q = __dmul_rn(t, rh);
   double r = __fma_rn(-h, q, t);
   q = __fma_rn(r, rh, q);
   r = __fma_rn(-h, q, t);
-  return __fma_rn(r, rh, q);
+  q = __fma_rn(r, rh, q);
+  const unsigned e = ((unsigned)__double2hiint(t) >> 20) & 0x7ffu;
+  if (t == 0.0) {
+    q = h > 0.0 ? t : -t;  // 0 / h is a signed zero
+  } else if (e - 323u >= 1400u) {  // |t| outside [2^-700, 2^700)
+    q = div_by_spacing_slow(t, h);
+  }
+  return q;
 }
 
 // div_by_spacing's range for the divisor (host check)
