@@ -21,9 +21,12 @@ struct SbDivisor {
 };
 struct SbDivisors6 { SbDivisor d[6]; };  // x edge, x interior (2 h), y edge, y interior, z edge, z interior
 
-template <bool kPow2>
+// kPow2 = 1: all six divisors are powers of two; 0: reciprocal + two exact FMA corrections (bulk_pipe.cuh, the
+// divisors are inside its range); 2: IEEE division
+template <int kPow2>
 __device__ __forceinline__ double sb_div(double num, const SbDivisor& d) {
-  if (kPow2) return __dmul_rn(num, d.inv);
+  if (kPow2 == 1) return __dmul_rn(num, d.inv);
+  if (kPow2 == 0) return div_by_spacing(num, d.den, d.inv);
   if (num == 0.0) return d.den > 0.0 ? num : -num;  // signed zero without the division slow path
   return __ddiv_rn(num, d.den);
 }
@@ -38,7 +41,7 @@ static constexpr int kSbFieldBytes = kSbFRows * kSbFRow * 4;                    
 static constexpr int kSbStageBytes = ((3 * kSbFieldBytes + kSbRows * kSbCols) + 127) / 128 * 128;  // + mask tile
 static constexpr int kSbWarpBytes = 2 * kSbCols * 4 + kSbCols;  // per warp: two result rows and the fluid-voxel list
 
-template <bool kPow2>
+template <int kPow2>
 __global__ void __launch_bounds__(kSbThreads, 2) strain_vorticity_bulk_kernel(
     const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
     const uint8_t* __restrict__ mask, int nx, int ny, int nz, const SbDivisors6 dv, float* __restrict__ strain,
@@ -237,7 +240,9 @@ int launch_strain_vorticity_bulk(const float* u, const float* v, const float* w,
     kern<<<(unsigned)grid, kSbThreads, smem, s>>>(u, v, w, mask, nx, ny, nz, dv, strain, vort, tiles_x,     \
                                                   tiles_y, zseg, la);                                       \
   } while (0)
-  if (pow2) PTV_SB_LAUNCH(true); else PTV_SB_LAUNCH(false);
+  bool fast = true;
+  for (int c = 0; c < 6; ++c) fast = fast && spacing_ok(dv.d[c].den);
+  if (pow2) PTV_SB_LAUNCH(1); else if (fast) PTV_SB_LAUNCH(0); else PTV_SB_LAUNCH(2);
 #undef PTV_SB_LAUNCH
   count_launches(1);
   PTV_CUDA(cudaGetLastError());
