@@ -68,7 +68,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-all-voxel", action="store_true")
-    ap.add_argument("--no-halo-overlap", action="store_true", help="one interpolation launch per slab, halos afterwards")
+    ap.add_argument("--halo-overlap", action="store_true",
+                    help="interpolate the slab's boundary planes first and exchange halos behind the interior (3 launches)")
+    ap.add_argument("--no-halo-overlap", action="store_true", help=argparse.SUPPRESS)  # the default since round 2
     ap.add_argument("--cpu-sample-voxels", type=int, default=400_000)
     ap.add_argument("--parity-voxels", type=int, default=4000)
     ap.add_argument("--c5-frames", type=int, default=64)
@@ -401,7 +403,7 @@ def run_b200(args):
             e[0].record()
         res = hot_path_step(eng, points, values, ax, ax, ax, mask_slab, comm, method=method, k=k, out=out,
                             mark=(lambda label: e[marks[label]].record()) if record else None,
-                            overlap_halos=not args.no_halo_overlap)
+                            overlap_halos=args.halo_overlap and not args.no_halo_overlap)
         if record:
             e[3].record()
         keep.update(div=res.div, res=res)

@@ -24,10 +24,14 @@ class StepResult:
 
 def hot_path_step(eng: PTVEngine, points, values, ax_x, ax_y, ax_z, mask_slab, comm: SlabComm, method="idw",
                   k=50, idw_power=2.0, spacing=(1.0, 1.0, 1.0), out=None, out_dtype=torch.float32,
-                  rebuild=True, mark=None, overlap_halos=True) -> StepResult:
+                  rebuild=True, mark=None, overlap_halos=False) -> StepResult:
     """One pass over one PTV frame for this rank's z-slab.  ``ax_z`` is the FULL z axis; the slab is
     comm.z0:comm.z1.  ``mask_slab`` is the (nz_local, ny, nx) uint8 pore mask of the slab.  ``mark(label)``
-    is called after the hash build ("built") and after the last interpolation launch ("interpolated")."""
+    is called after the hash build ("built") and after the last interpolation launch ("interpolated").
+    ``overlap_halos``: interpolate the slab's first and last 32 planes first and let the halo exchange travel while
+    the interior is searched.  Off by default: the exchange is 10 MB over NVLink (0.1 ms exposed), while three
+    launches instead of one cost three kernel tails -- measured at 8 GPUs 35.0 ms per frame without, 35.8 ms with
+    (profiles/r02_v4_bench_c4_n8*.json), at 2 GPUs 136.2 vs 136.7 ms."""
     mark = mark or (lambda label: None)
     slab_hash = rebuild and comm.world > 1 and method in ("idw", "sibson")
     if slab_hash:
