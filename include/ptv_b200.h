@@ -217,6 +217,14 @@ int ptv_strain_vorticity(const void* d_u, const void* d_v, const void* d_w, cons
                          int ny, int nz, double dx, double dy, double dz, int dtype, void* d_strain,
                          void* d_vorticity, void* stream);
 
+/* z-slab form for a grid sharded over GPUs: d_below / d_above are the (3, ny, nx) planes (u, v, w) of the
+ * z-neighbours just outside the slab (NULL = that side is a face of the whole domain), so the slab's outer
+ * planes get np.gradient's central differences.  float32 fields with nx % 16 == 0 and 16-byte aligned buffers
+ * only (PTV_ERR_INVALID otherwise: pad the slab with its halo planes and call ptv_strain_vorticity). */
+int ptv_strain_vorticity_slab(const void* d_u, const void* d_v, const void* d_w, const uint8_t* d_mask, int nx,
+                              int ny, int nz, double dx, double dy, double dz, const void* d_below,
+                              const void* d_above, int dtype, void* d_strain, void* d_vorticity, void* stream);
+
 /* ---- projection cleaning (physics.py:55-209).  ptv_poisson_lsqr solves
  *      A phi = div - mean(div[mask]) with the matrix-free masked 7-point Laplacian of
  *      build_laplacian_matrix (physics.py:55-108) by LSQR with SciPy's recurrences and stopping rules

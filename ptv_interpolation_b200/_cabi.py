@@ -26,7 +26,7 @@ EXPORTS = [
     "ptv_hash_create", "ptv_hash_destroy", "ptv_hash_build", "ptv_hash_build_slab", "ptv_hash_clip_violations", "ptv_hash_clip_violations_to", "ptv_hash_info", "ptv_knn_interp", "ptv_knn_stats", "ptv_knn_fail_reasons", "ptv_knn_work_stats", "ptv_linear_stats", "ptv_knn_points", "ptv_outlier_filter",
     "ptv_mask_gather", "ptv_boundary_voxels", "ptv_boundary_voxels_ws", "ptv_boundary_workspace_bytes", "ptv_apply_mask", "ptv_divergence", "ptv_divergence_flux",
     "ptv_flux_profiles", "ptv_strain_vorticity", "ptv_poisson_workspace_bytes", "ptv_poisson_lsqr", "ptv_projection_correct",
-    "ptv_interpolate_host", "ptv_selftest_division",
+    "ptv_interpolate_host", "ptv_selftest_division", "ptv_strain_vorticity_slab",
 ]
 
 
@@ -94,6 +94,8 @@ def _declare(lib):
                                         vp]
     lib.ptv_flux_profiles.restype = i32
     lib.ptv_flux_profiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.ptv_strain_vorticity_slab.restype = i32
+    lib.ptv_strain_vorticity_slab.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, vp, vp, i32, vp, vp, vp]
     lib.ptv_selftest_division.restype = i32
     lib.ptv_selftest_division.argtypes = [f64, i64, C.c_uint64, C.POINTER(i64)]
     lib.ptv_strain_vorticity.restype = i32

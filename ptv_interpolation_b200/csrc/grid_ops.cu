@@ -9,7 +9,8 @@
 namespace ptv {
 
 int launch_strain_vorticity_bulk(const float* u, const float* v, const float* w, const uint8_t* mask, int nx, int ny,
-                                 int nz, double dx, double dy, double dz, float* strain, float* vort, cudaStream_t s);
+                                 int nz, double dx, double dy, double dz, float* strain, float* vort, const float* below,
+                                 const float* above, cudaStream_t s);
 
 // ------------------------------------------------------------------ mask gather (a2)
 // out[z,y,x] = raw[iz[z], iy[y], ix[x]] != 0, 0 where any index is -1 (out of bounds ->
@@ -560,7 +561,7 @@ extern "C" int ptv_strain_vorticity(const void* d_u, const void* d_v, const void
   }
   if (dtype == PTV_F32) {  // z-marching kernel over bulk-copied plane tiles (strain_bulk.cu) where shape and alignment allow
     const int rc = launch_strain_vorticity_bulk((const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dx,
-                                                dy, dz, (float*)d_strain, (float*)d_vorticity, (cudaStream_t)stream);
+                                                dy, dz, (float*)d_strain, (float*)d_vorticity, nullptr, nullptr, (cudaStream_t)stream);
     if (rc != -1) return rc;
   }
   const int64_t n = (int64_t)nx * ny * nz;
@@ -833,5 +834,29 @@ extern "C" int ptv_flux_profiles(const void* d_u, const void* d_v, const void* d
   if (dtype == PTV_F32) return flux_launch<float>(d_u, d_v, d_w, nx, ny, nz, d_qxy, d_qxz, d_qyz, (cudaStream_t)stream);
   if (dtype == PTV_F64) return flux_launch<double>(d_u, d_v, d_w, nx, ny, nz, d_qxy, d_qxz, d_qyz, (cudaStream_t)stream);
   set_error("ptv_flux_profiles: bad dtype");
+  return PTV_ERR_INVALID;
+}
+
+// z-slab form (one rank's planes of a sharded grid): the planes just below / above the slab come from the
+// z-neighbours as (3, ny, nx) buffers (u, v, w) so that the slab's first and last planes get np.gradient's central
+// differences; NULL = that side is a face of the whole domain.  Served by the bulk-tile kernel only; shapes it
+// cannot take return PTV_ERR_INVALID and the caller pads the slab with its halo planes instead (engine.py does).
+extern "C" int ptv_strain_vorticity_slab(const void* d_u, const void* d_v, const void* d_w, const uint8_t* d_mask, int nx,
+                                         int ny, int nz, double dx, double dy, double dz, const void* d_below,
+                                         const void* d_above, int dtype, void* d_strain, void* d_vorticity, void* stream) {
+  if (!d_u || !d_v || !d_w) { set_error("ptv_strain_vorticity_slab: NULL argument"); return PTV_ERR_INVALID; }
+  if (!d_strain && !d_vorticity) { set_error("ptv_strain_vorticity_slab: nothing to compute"); return PTV_ERR_INVALID; }
+  const int nz_ext = nz + (d_below ? 1 : 0) + (d_above ? 1 : 0);
+  if (nx < 2 || ny < 2 || nz < 1 || nz_ext < 2) {
+    set_error("Shape of array too small to calculate a numerical gradient, at least (edge_order + 1) elements are required.");
+    return PTV_ERR_INVALID;
+  }
+  if (dtype == PTV_F32) {
+    const int rc = launch_strain_vorticity_bulk((const float*)d_u, (const float*)d_v, (const float*)d_w, d_mask, nx, ny, nz, dx,
+                                                dy, dz, (float*)d_strain, (float*)d_vorticity, (const float*)d_below,
+                                                (const float*)d_above, (cudaStream_t)stream);
+    if (rc != -1) return rc;
+  }
+  set_error("ptv_strain_vorticity_slab: needs float32 fields with nx % 16 == 0 and 16-byte aligned buffers");
   return PTV_ERR_INVALID;
 }

@@ -45,7 +45,8 @@ template <int kPow2>
 __global__ void __launch_bounds__(kSbThreads, 2) strain_vorticity_bulk_kernel(
     const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
     const uint8_t* __restrict__ mask, int nx, int ny, int nz, const SbDivisors6 dv, float* __restrict__ strain,
-    float* __restrict__ vort, int tiles_x, int tiles_y, int zseg, int la) {
+    float* __restrict__ vort, const float* __restrict__ below, const float* __restrict__ above, int tiles_x,
+    int tiles_y, int zseg, int la) {
   extern __shared__ __align__(128) unsigned char sb_smem[];
   __shared__ __align__(8) uint64_t full_bar[kSbStages], empty_bar[kSbStages];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -80,21 +81,25 @@ __global__ void __launch_bounds__(kSbThreads, 2) strain_vorticity_bulk_kernel(
     const uint32_t bar = smem_addr(&full_bar[s]);
     if (k >= kSbStages) mbar_wait(smem_addr(&empty_bar[s]), ((k / kSbStages) & 1) ^ 1);
     const int zp = zs - 1 + k;
-    if (zp < 0 || zp >= nz) {  // no such plane: the step still completes its barrier phase
+    // the planes just outside the slab come from the z-neighbours' halo buffers ((3, ny, nx): u, v, w), if any
+    const float* halo = zp < 0 ? below : (zp >= nz ? above : nullptr);
+    const bool inside = zp >= 0 && zp < nz;
+    if (!inside && halo == nullptr) {  // no such plane: the step still completes its barrier phase
       if (lane == 0) mbar_arrive(bar);
       return;
     }
-    if (lane == 0) mbar_expect_tx(bar, 3u * nfrows * frow_bytes + nmrows * (uint32_t)cw);
+    if (lane == 0) mbar_expect_tx(bar, 3u * nfrows * frow_bytes + (inside ? nmrows * (uint32_t)cw : 0u));
     __syncwarp();
     const uint32_t sb = smem_addr(sb_smem + (size_t)s * kSbStageBytes);
     for (int i = lane; i < 3 * kSbFRows + kSbRows; i += 32) {
       if (i < 3 * kSbFRows) {
         const int f = i / kSbFRows, r = i - f * kSbFRows;
         if (r >= ra && r <= rb) {
-          const float* src = (f == 0 ? u : f == 1 ? v : w) + (int64_t)zp * plane + (int64_t)(y0 - 1 + r) * nx + (x0 - left);
+          const float* pl = inside ? (f == 0 ? u : f == 1 ? v : w) + (int64_t)zp * plane : halo + (int64_t)f * plane;
+          const float* src = pl + (int64_t)(y0 - 1 + r) * nx + (x0 - left);
           bulk_g2s(sb + (uint32_t)(f * kSbFieldBytes + (r * kSbFRow + 4 - left) * 4), src, frow_bytes, bar);
         }
-      } else {
+      } else if (inside) {
         const int r = i - 3 * kSbFRows;
         if ((uint32_t)r < nmrows)
           bulk_g2s(sb + (uint32_t)(3 * kSbFieldBytes + r * kSbCols), mask + (int64_t)zp * plane + (int64_t)(y0 + r) * nx + x0,
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(kSbThreads, 2) strain_vorticity_bulk_kernel(
     const int zc = zs + k - 2;  // centre plane
     const int sa = (k - 2) % kSbStages, sc = (k - 1) % kSbStages, sn = k % kSbStages;
     const float* tc = reinterpret_cast<const float*>(sb_smem + (size_t)sc * kSbStageBytes);
-    const bool z_first = zc == 0, z_last = zc == nz - 1;
+    const bool z_first = zc == 0 && below == nullptr, z_last = zc == nz - 1 && above == nullptr;  // true domain faces
     const float* tlo = z_first ? tc : reinterpret_cast<const float*>(sb_smem + (size_t)sa * kSbStageBytes);
     const float* thi = z_last ? tc : reinterpret_cast<const float*>(sb_smem + (size_t)sn * kSbStageBytes);
     const SbDivisor dzz = (z_first || z_last) ? dze : dzi;
@@ -211,10 +216,11 @@ static SbDivisor sb_divisor(double den, bool* pow2) {
 
 // Returns PTV_OK after launching, or -1 if shape / alignment rule the bulk path out (the caller falls back).
 int launch_strain_vorticity_bulk(const float* u, const float* v, const float* w, const uint8_t* mask, int nx, int ny,
-                                 int nz, double dx, double dy, double dz, float* strain, float* vort, cudaStream_t s) {
+                                 int nz, double dx, double dy, double dz, float* strain, float* vort, const float* below,
+                                 const float* above, cudaStream_t s) {
   const auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (tuning().stencil_bulk == 0 || nx % 16 != 0 || !al16(u) || !al16(v) || !al16(w) || !al16(mask) || !al16(strain) ||
-      !al16(vort))
+      !al16(vort) || !al16(below) || !al16(above))
     return -1;
   bool pow2 = true;
   SbDivisors6 dv;
@@ -237,8 +243,8 @@ int launch_strain_vorticity_bulk(const float* u, const float* v, const float* w,
   do {                                                                                                      \
     auto kern = strain_vorticity_bulk_kernel<P2>;                                                           \
     PTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    kern<<<(unsigned)grid, kSbThreads, smem, s>>>(u, v, w, mask, nx, ny, nz, dv, strain, vort, tiles_x,     \
-                                                  tiles_y, zseg, la);                                       \
+    kern<<<(unsigned)grid, kSbThreads, smem, s>>>(u, v, w, mask, nx, ny, nz, dv, strain, vort, below, above, \
+                                                  tiles_x, tiles_y, zseg, la);                              \
   } while (0)
   bool fast = true;
   for (int c = 0; c < 6; ++c) fast = fast && spacing_ok(dv.d[c].den);

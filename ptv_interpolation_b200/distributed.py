@@ -103,6 +103,24 @@ class SlabComm:
             req.wait()
         return handle[1]
 
+    def exchange_planes(self, first: torch.Tensor, last: torch.Tensor):
+        """Generic one-plane halo exchange: ``first`` / ``last`` are this rank's outermost planes (any shape, e.g. the
+        (3, ny, nx) stack of u, v, w for the gradient stencils).  Returns (below, above): the lower neighbour's
+        ``last`` and the upper neighbour's ``first`` (None at the domain faces)."""
+        if self.world == 1:
+            return None, None
+        first, last = first.contiguous(), last.contiguous()
+        ops, below, above = [], None, None
+        if self.lower is not None:
+            below = torch.empty_like(first)
+            ops += [dist.P2POp(dist.isend, first, self.lower, self.group), dist.P2POp(dist.irecv, below, self.lower, self.group)]
+        if self.upper is not None:
+            above = torch.empty_like(last)
+            ops += [dist.P2POp(dist.isend, last, self.upper, self.group), dist.P2POp(dist.irecv, above, self.upper, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        return below, above
+
     def reduce_profiles_(self, acc: torch.Tensor):
         """ONE sum-all-reduce for everything the stencil pass accumulates: ``acc`` is the flat float64 buffer
         [sum|div|, n_fluid | Q_xy[nz] (each rank fills its own planes, zeros elsewhere) | Q_xz[ny] | Q_yz[nx]]."""

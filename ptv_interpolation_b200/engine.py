@@ -379,12 +379,16 @@ class PTVEngine:
             return div, stats, qxy, qxz, qyz
         return div, stats, qxy, qxz, qyz, acc
 
-    def strain_vorticity(self, u, v, w, dx, dy, dz, mask=None, strain=True, vorticity=True):
-        """(shear-rate magnitude, vorticity magnitude) of the field; either may be skipped (None)."""
+    def strain_vorticity(self, u, v, w, dx, dy, dz, mask=None, strain=True, vorticity=True, below=None, above=None):
+        """(shear-rate magnitude, vorticity magnitude) of the field; either may be skipped (None).
+        ``below`` / ``above``: for a z-slab of a sharded grid, the (3, ny, nx) planes (u, v, w) of the z-neighbours
+        just outside the slab (``SlabComm.exchange_planes``); None = a face of the whole domain."""
         nz, ny, nx = u.shape
         if mask is not None and mask.dtype == torch.bool:
             mask = mask.view(torch.uint8)
         u, v, w = u.contiguous(), v.contiguous(), w.contiguous()
+        if below is not None or above is not None:
+            return self._strain_vorticity_slab(u, v, w, dx, dy, dz, mask, strain, vorticity, below, above)
         s = torch.empty_like(u) if strain else None
         o = torch.empty_like(u) if vorticity else None
         with torch.cuda.device(self.device):
@@ -392,6 +396,39 @@ class PTVEngine:
                                                       float(dy), float(dz), _dtype_code(u.dtype), _ptr(s), _ptr(o),
                                                       self._stream()))
         return s, o
+
+    def _strain_vorticity_slab(self, u, v, w, dx, dy, dz, mask, strain, vorticity, below, above):
+        nz, ny, nx = u.shape
+        for h in (below, above):
+            if h is not None and (tuple(h.shape) != (3, ny, nx) or h.dtype != u.dtype):
+                raise ValueError("halo planes must be (3, ny, nx) tensors of the fields' dtype")
+        below = None if below is None else below.contiguous()
+        above = None if above is None else above.contiguous()
+        s = torch.empty_like(u) if strain else None
+        o = torch.empty_like(u) if vorticity else None
+        if u.dtype == torch.float32 and nx % 16 == 0:
+            with torch.cuda.device(self.device):
+                rc = self.lib.ptv_strain_vorticity_slab(_ptr(u), _ptr(v), _ptr(w), _ptr(mask), nx, ny, nz, float(dx),
+                                                        float(dy), float(dz), _ptr(below), _ptr(above),
+                                                        _dtype_code(u.dtype), _ptr(s), _ptr(o), self._stream())
+            if rc == 0:
+                return s, o
+        # shapes the slab kernel does not take: the slab padded with its halo planes through the whole-grid kernels;
+        # the padded planes' own results (one-sided differences) are dropped
+        lo, hi = (0 if below is None else 1), (0 if above is None else 1)
+
+        def pad(f, i):
+            parts = ([below[i:i + 1]] if lo else []) + [f] + ([above[i:i + 1]] if hi else [])
+            return torch.cat(parts, dim=0)
+
+        mp = None
+        if mask is not None:
+            ones = torch.ones((1, ny, nx), dtype=mask.dtype, device=mask.device)
+            mp = torch.cat(([ones] if lo else []) + [mask] + ([ones] if hi else []), dim=0)
+        sp, op = self.strain_vorticity(pad(u, 0), pad(v, 1), pad(w, 2), dx, dy, dz, mask=mp, strain=strain,
+                                       vorticity=vorticity)
+        cut = slice(lo, lo + nz)
+        return (None if sp is None else sp[cut].contiguous()), (None if op is None else op[cut].contiguous())
 
     def poisson_lsqr(self, div, mask, dx, dy, dz, damp=1e-8, atol=1e-10, btol=1e-10, conlim=1e8, iter_lim=3000):
         """LSQR solve of the masked Laplacian system for div - mean(div[mask]) (physics.py:180-186).

@@ -110,6 +110,19 @@ def _worker(rank, world, port, shape, tmp):
         assert np.allclose(acc[2 + nz:2 + nz + ny].numpy(), v.sum(axis=(0, 2)), rtol=1e-12, atol=1e-12)
         assert np.allclose(acc[2 + nz + ny:].numpy(), u.sum(axis=(0, 1)), rtol=1e-12, atol=1e-12)
         assert abs(acc[0].item() / acc[1].item() - rp.mean_abs_div(ref, m)) < 1e-13
+        # gradient stencils on slabs (velocity_analysis.py:10-120): one (3, ny, nx) plane of u, v, w from each
+        # z-neighbour makes the slab's result equal to the whole-grid result
+        stack = torch.from_numpy(np.stack([u[z0:z1], v[z0:z1], w[z0:z1]]))
+        below, above = comm.exchange_planes(stack[:, 0], stack[:, -1])
+        assert (below is None) == (rank == 0) and (above is None) == (rank == world - 1)
+        if below is not None:
+            assert np.array_equal(below.numpy(), np.stack([u[z0 - 1], v[z0 - 1], w[z0 - 1]]))
+        if above is not None:
+            assert np.array_equal(above.numpy(), np.stack([u[z1], v[z1], w[z1]]))
+        if z1 - z0 + lo + hi >= 2:
+            s_ext = rp.compute_strain_rate(u[ext], v[ext], w[ext], 1.0, 2.0, 0.5)
+            s_ref = rp.compute_strain_rate(u, v, w, 1.0, 2.0, 0.5)
+            assert np.array_equal(s_ext[lo:s_ext.shape[0] - hi], s_ref[z0:z1])
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -810,6 +810,31 @@ def test_strain_vorticity_bulk_kernel(shape, h):
     assert torch.equal(s0, s1) and torch.equal(o0, o1)
 
 
+@pytest.mark.parametrize("shape,dtype", [((12, 9, 32), np.float32), ((7, 5, 16), np.float32), ((9, 6, 10), np.float32),
+                                         ((8, 4, 16), np.float64)])
+def test_strain_vorticity_slabs_with_halos_match_whole(shape, dtype):
+    """A grid cut into z-slabs, each with the (3, ny, nx) planes of its z-neighbours: the slab results concatenate to
+    the whole-grid result bit for bit (kernel halos for float32 / nx % 16 == 0, padded slabs otherwise)."""
+    rng = np.random.default_rng(shape[0] * shape[2])
+    u, v, w = (rng.normal(size=shape).astype(dtype) for _ in range(3))
+    m = rng.random(shape) > 0.35
+    h = (1.25, 0.75, 2.0)
+    eng = PTVEngine()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    s_all, o_all = eng.strain_vorticity(t(u), t(v), t(w), *h, mask=t(m))
+    cuts = [0, 1, 4, shape[0] - 2, shape[0]]
+    s_parts, o_parts = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        below = t(np.stack([u[a - 1], v[a - 1], w[a - 1]])) if a > 0 else None
+        above = t(np.stack([u[b], v[b], w[b]])) if b < shape[0] else None
+        s, o = eng.strain_vorticity(t(u[a:b]), t(v[a:b]), t(w[a:b]), *h, mask=t(m[a:b]), below=below, above=above)
+        s_parts.append(s)
+        o_parts.append(o)
+    assert torch.equal(torch.cat(s_parts), s_all) and torch.equal(torch.cat(o_parts), o_all)
+    ref = rp.compute_strain_rate(u.astype(np.float64), v.astype(np.float64), w.astype(np.float64), *h, mask=m)
+    assert np.array_equal(s_all.cpu().numpy(), ref.astype(dtype))
+
+
 # ------------------------------------------------------------------ N2: projection cleaning
 def test_projection_cleaning_golden(golden_dir, capsys):
     g = np.load(os.path.join(golden_dir, "case_h_projection.npz"))
