@@ -413,6 +413,8 @@ class PTVEngine:
                                                         _dtype_code(u.dtype), _ptr(s), _ptr(o), self._stream())
             if rc == 0:
                 return s, o
+            if rc != 1:  # anything but "this shape / alignment is not served" (PTV_ERR_INVALID) is a real error
+                _cabi.check(rc)
         # shapes the slab kernel does not take: the slab padded with its halo planes through the whole-grid kernels;
         # the padded planes' own results (one-sided differences) are dropped
         lo, hi = (0 if below is None else 1), (0 if above is None else 1)
