@@ -22,6 +22,8 @@ d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
 
 
 def num(key):
+    if key not in d:  # a reduced section set was captured
+        return float("nan")
     u, v = d[key]
     x = float(v.replace(",", ""))
     scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1.0, "us": 1e-3, "ms": 1.0, "s": 1e3,
@@ -40,9 +42,9 @@ prof = {
     "kernel_source_sha256": sha,
     "capture": os.path.basename(rep),
     "kernel_ms_under_ncu": num("gpu__time_duration.sum"),
-    "registers_per_thread": int(num("launch__registers_per_thread")),
+    "registers_per_thread": int(num("launch__registers_per_thread")) if "launch__registers_per_thread" in d else None,
     "dynamic_smem_bytes": num("launch__shared_mem_per_block_dynamic"),
-    "grid_size": int(num("launch__grid_size")),
+    "grid_size": int(num("launch__grid_size")) if "launch__grid_size" in d else None,
     "warp_inst_per_launch": num("smsp__inst_executed.sum"),
     "threads_per_inst": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
     "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
