@@ -263,3 +263,21 @@ def test_hull_candidate_rule_keeps_every_hull_vertex(kind):
         assert keep.sum() <= 0.2 * len(pts)
     if kind == "lattice_faces":  # the interior of the flat faces goes, only their outline can stay
         assert keep.sum() <= 8 * 9 + 40
+
+
+def test_exact_division_by_spacing_cpu_restatement():
+    """oracle/div_exact.c restates the stencil kernels' division by a grid spacing (reciprocal + two exact-residual FMA
+    corrections, csrc/bulk_pipe.cuh) on the CPU: every quotient must be the IEEE one the reference computes
+    (physics.py:26-53, np.gradient).  The GPU twin of this test is ptv_selftest_division."""
+    import ctypes as C
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    lib_path = os.path.join(here, "_build", "libdiv_exact.so")
+    if not os.path.exists(lib_path):
+        subprocess.run(["make", "-s", "-C", here], check=True)
+    lib = C.CDLL(lib_path)
+    lib.div_exact_mismatches.restype = C.c_int64
+    lib.div_exact_mismatches.argtypes = [C.c_double, C.c_int64, C.c_uint64]
+    for h in (2.00625, 4.0125, 1.25, 0.75, 3.0, 0.1, 1e-3, 7.0, -2.00625, 1.9999999999999998, 1.0000000000000002,
+              1.0 / 3.0, 123456.789):
+        assert lib.div_exact_mismatches(h, 2_000_000, 12345) == 0, h
